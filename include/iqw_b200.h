@@ -1,0 +1,133 @@
+/* iqw_b200.h -- C-ABI of the B200-native iqwaveform spectral-analysis hot path.
+ *
+ * The reference (dgkuester/iqwaveform 0.52.0, pure Python) has no FFI: its "backend boundary" is
+ * the per-call switch on the array type (numpy -> scipy.fft / numpy, cupy -> cuFFT / cupy) inside
+ * four public functions.  Each entry point below replaces the device-side work that one of those
+ * functions delegates to its array backend; the Python package `iqwaveform_b200` keeps the
+ * reference's signatures on top of them (see INTEGRATION.md for the ctypes binding a reference
+ * maintainer would add).  Paths are relative to /root/reference/src/iqwaveform/.
+ *
+ * Conventions
+ *  - every pointer named d_* is DEVICE memory on the current CUDA device; the caller owns all
+ *    buffers, including workspaces; nothing here allocates or frees caller-visible memory (the
+ *    library keeps one small immutable twiddle table per (device, nfft), built on first use)
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
+ *  - complex64 is interleaved (re, im) float32; sizes are in ELEMENTS unless named *_bytes
+ *  - return value: 0 on success, a negative iqw_status otherwise; iqw_last_error() returns a
+ *    thread-local description of the last failure; no C++ exception crosses this boundary
+ */
+#ifndef IQW_B200_H
+#define IQW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IQW_ABI_VERSION 1
+
+typedef enum iqw_status {
+    IQW_OK = 0,
+    IQW_ERR_INVALID = -1,      /* bad argument (null pointer, size, range) */
+    IQW_ERR_UNSUPPORTED = -2,  /* valid in the reference but not built here (e.g. nfft not 2^k) */
+    IQW_ERR_CUDA = -3,         /* a CUDA runtime call failed; text in iqw_last_error() */
+    IQW_ERR_WORKSPACE = -4     /* workspace too small */
+} iqw_status;
+
+typedef enum iqw_stft_mode {
+    IQW_STFT_COMPLEX = 0,  /* complex64 STFT                    (fourier.py:927 stft)            */
+    IQW_STFT_POWER = 1,    /* float32 |X|^2                     (fourier.py:1203 spectrogram)    */
+    IQW_STFT_DB = 2        /* float32 10*log10(|X|^2 + eps)     (power_analysis.py:168 powtodB)  */
+} iqw_stft_mode;
+
+/* statistic kinds for iqw_time_stats_f32 / iqw_bin_power_c64 (power_analysis.py:73-101) */
+typedef enum iqw_stat_kind {
+    IQW_STAT_QUANTILE = 0, /* numpy 'linear' quantile: lerp(a[rank_lo], a[rank_hi], gamma)        */
+    IQW_STAT_MEAN = 1,     /* 'mean' and 'rms'                                                    */
+    IQW_STAT_MAX = 2,      /* 'max' and 'peak'                                                    */
+    IQW_STAT_MIN = 3,
+    IQW_STAT_MEDIAN = 4    /* numpy median: 0.5*(a[(n-1)/2] + a[n/2])                             */
+} iqw_stat_kind;
+
+/* one requested statistic (one output row).  For QUANTILE the host supplies the float32 index
+ * arithmetic of numpy's 'linear' method -- rank_lo = floor((n-1)*q), rank_hi, gamma = frac --
+ * computed exactly as numpy does (python: iqwaveform_b200._plan.quantile_plan). */
+typedef struct iqw_stat {
+    int32_t kind;     /* iqw_stat_kind */
+    int64_t rank_lo;  /* QUANTILE only, 0-based order statistic */
+    int64_t rank_hi;
+    float gamma;
+} iqw_stat;
+
+int iqw_abi_version(void);
+const char* iqw_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 1: overlapped-frame gather * window -> FFT -> {complex | |X|^2 | dB} -> band trim.
+ * Replaces fourier.py:545-581 (_stack_stft_windows) + 1016-1028 (no-overlap branch) +
+ * fourier.py:200-218 (fft) + power_analysis.py:251-255 (envtopow) + 196-204 (powtodB) +
+ * the band slice of fourier.py:1289-1295, in ONE pass over the samples.
+ *
+ *   d_x           (n_channels, n_samples) complex64, row stride x_channel_stride elements
+ *   d_window      nfft float32 coefficients that multiply a frame.  The caller folds in the
+ *                 (-1)^n fft-shift, the 1/nfft and (norm=None) the COLA scale, exactly as the
+ *                 reference does on the host (fourier.py:1002-1010, 1033, 571-580)
+ *   nfft          power of two, 16 <= nfft <= 8192 (larger: IQW_ERR_UNSUPPORTED)
+ *   hop           nfft - noverlap >= 1;  frame m covers samples [m*hop, m*hop + nfft)
+ *   n_frames      T <= (n_samples - nfft)/hop + 1
+ *   bin_lo,bin_hi output bins [bin_lo, bin_hi) of the fft-shifted spectrum (0, nfft = all)
+ *   d_out         (n_channels, n_frames, bin_hi-bin_lo), complex64 (COMPLEX) or float32,
+ *                 C-contiguous, channel stride out_channel_stride elements
+ */
+int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,
+                 const float* d_window, int32_t nfft, int64_t hop, int64_t n_frames, int32_t mode,
+                 float eps, int32_t bin_lo, int32_t bin_hi, void* d_out,
+                 int64_t out_channel_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 2: statistics over the time axis of a (n_channels, n_rows, n_cols) float32 matrix
+ * (rows = frames, cols = bins): exact order statistics + numpy 'linear' lerp, mean, max, min.
+ * Replaces fourier.py:1311-1325 (np.quantile / stat ufuncs over axis) and, with to_dB != 0,
+ * the in-place powtodB of fourier.py:1298-1299 (applied to the selected order statistics, which
+ * is identical because 10*log10(p + eps) is monotone; 'mean' averages the dB values of every
+ * element, as the reference does).
+ *
+ *   d_p            input matrix; row stride = n_cols, channel stride p_channel_stride elements
+ *   stats          HOST array of n_stats requests (copied during the call)
+ *   d_out          (n_channels, n_stats, n_cols) float32, C-contiguous
+ *   d_workspace    >= iqw_time_stats_workspace_bytes(...) bytes, 256-byte aligned
+ */
+size_t iqw_time_stats_workspace_bytes(int64_t n_channels, int64_t n_rows, int64_t n_cols,
+                                      int32_t n_stats);
+int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t n_rows, int64_t n_cols,
+                       int64_t p_channel_stride, const iqw_stat* stats, int32_t n_stats,
+                       int32_t to_dB, float eps, float* d_out, void* d_workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 3: per-bin envelope power of contiguous bins of bin_len samples.
+ * Replaces power_analysis.py:380-385 (to_blocks + envtopow + mean/max/min detector).
+ *
+ *   d_x        (n_channels, >= n_bins*bin_len) complex64, row stride x_channel_stride elements
+ *   d_mean / d_max / d_min   each NULL or (n_channels, n_bins) float32
+ *   d_workspace  >= iqw_bin_power_workspace_bytes(...) bytes, 256-byte aligned (only touched when
+ *                there are too few bins to fill the GPU and bins are split across CTAs)
+ */
+size_t iqw_bin_power_workspace_bytes(int64_t n_channels, int64_t bin_len, int64_t n_bins);
+int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_channel_stride,
+                      int64_t bin_len, int64_t n_bins, float* d_mean, float* d_max, float* d_min,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* |x|^2 of (n_channels, n_bins, bin_len) complex64 written TRANSPOSED as float32
+ * (n_channels, bin_len, n_bins), so that the median / quantile detectors of iq_to_bin_power
+ * (power_analysis.py:382-385 with kind='median' or a float) run through iqw_time_stats_f32,
+ * whose statistics axis is the row axis.  Replaces power_analysis.py:251-255 for that case. */
+int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_channel_stride,
+                                int64_t bin_len, int64_t n_bins, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQW_B200_H */

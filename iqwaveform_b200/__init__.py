@@ -1,0 +1,21 @@
+"""iqwaveform_b200 -- B200-native spectral-analysis hot path of dgkuester/iqwaveform.
+
+Drop-in (same names, arguments, error behaviour) for
+
+    iqwaveform.fourier.stft / spectrogram / power_spectral_density (= persistence_spectrum)
+    iqwaveform.power_analysis.iq_to_bin_power
+
+backed by hand-written sm_100a CUDA kernels behind the C-ABI in ``include/iqw_b200.h``.
+Importing the package loads ``libiqw_b200.so`` and fails loudly when it is missing: there is no
+CPU fallback.
+"""
+from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is absent)
+from . import fourier, power_analysis
+from .fourier import (stft, spectrogram, power_spectral_density, persistence_spectrum, fftfreq,
+                      get_window, equivalent_noise_bandwidth, time_statistics)
+from .power_analysis import iq_to_bin_power
+
+__version__ = '0.1.0'
+__all__ = ['fourier', 'power_analysis', 'stft', 'spectrogram', 'power_spectral_density',
+           'persistence_spectrum', 'fftfreq', 'get_window', 'equivalent_noise_bandwidth',
+           'time_statistics', 'iq_to_bin_power']

@@ -1,0 +1,233 @@
+// fft_core.cuh -- register-resident mixed-radix (16/8/4/2) Stockham FFT building blocks.
+//
+// Replaces, inside the fused STFT kernel, the reference's batched FFT call
+// (/root/reference/src/iqwaveform/fourier.py:200-218, called from fourier.py:1044): forward,
+// unnormalised, complex fp32, along the frame axis.
+//
+// Everything here is __host__ __device__ so that tests/host/fft_emulate.cpp can run the exact same
+// butterfly / twiddle / index code thread-by-thread on the CPU (there is no GPU in the build
+// container) and compare it with a float64 DFT.
+//
+// Algorithm (autosort Stockham, decimation in time).  N = R_0 * R_1 * ... * R_{P-1}.  Pass p has
+// radix R = R_p and Ns = R_0*...*R_{p-1}.  Butterfly j (0 <= j < N/R) of pass p
+//     reads    in[j + r*N/R]                          r = 0..R-1
+//     scales   by W_{Ns*R}^{r*(j mod Ns)}             (nothing in pass 0, Ns = 1)
+//     does     an R-point DFT
+//     writes   out[(j / Ns)*Ns*R + (j mod Ns) + r*Ns]
+// Input and output are both in natural order; pass 0 reads global memory (stride N/R across r,
+// unit stride across j => coalesced) and the last pass writes bins j + r*N/R (coalesced).
+#pragma once
+
+#if defined(__CUDACC__)
+#define IQW_HD __host__ __device__ __forceinline__
+#include <cuda_runtime.h>
+#else
+#define IQW_HD inline
+#include <cmath>
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+namespace iqw {
+
+// ------------------------------------------------------------------------------------------
+// compile-time plan: radices per log2(N).  E = complex elements held per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPasses = 4;
+
+IQW_HD constexpr int plan_radix(int log2n, int p) {
+    // clang-format off
+    switch (log2n) {
+        case 4:  return p == 0 ? 16 : 1;
+        case 5:  return p == 0 ? 8  : p == 1 ? 4 : 1;
+        case 6:  return p <= 1 ? 8 : 1;
+        case 7:  return p == 0 ? 16 : p == 1 ? 8 : 1;
+        case 8:  return p <= 1 ? 16 : 1;
+        case 9:  return p <= 2 ? 8 : 1;
+        case 10: return p <= 1 ? 16 : p == 2 ? 4 : 1;
+        case 11: return p <= 1 ? 16 : p == 2 ? 8 : 1;
+        case 12: return p <= 2 ? 16 : 1;
+        case 13: return p <= 1 ? 16 : p == 2 ? 8 : p == 3 ? 4 : 1;
+        default: return 1;
+    }
+    // clang-format on
+}
+
+IQW_HD constexpr int plan_passes(int log2n) {
+    int n = 0;
+    for (int p = 0; p < kMaxPasses; ++p) n += plan_radix(log2n, p) > 1 ? 1 : 0;
+    return n;
+}
+
+IQW_HD constexpr int plan_elems(int log2n) {   // elements per thread
+    return log2n == 5 || log2n == 6 ? 8 : 16;
+}
+
+IQW_HD constexpr int plan_ns(int log2n, int p) {   // product of the radices before pass p
+    int ns = 1;
+    for (int q = 0; q < p; ++q) ns *= plan_radix(log2n, q);
+    return ns;
+}
+
+// twiddle table: pass p >= 1 owns (R_p - 1) * Ns_p entries, entry (r-1)*Ns + i = W_{Ns*R}^{r*i}
+IQW_HD constexpr int plan_tw_offset(int log2n, int p) {
+    int off = 0;
+    for (int q = 1; q < p; ++q) off += (plan_radix(log2n, q) - 1) * plan_ns(log2n, q);
+    return off;
+}
+IQW_HD constexpr int plan_tw_size(int log2n) { return plan_tw_offset(log2n, plan_passes(log2n)); }
+
+// shared-memory exchange index with one pad element every 16 (kills the 16-way conflict of the
+// stride-R stores after pass 0; see DESIGN.md "bank conflicts")
+IQW_HD constexpr int pad_index(int i) { return i + (i >> 4); }
+IQW_HD constexpr int padded_size(int n) { return n + (n >> 4); }
+
+// ------------------------------------------------------------------------------------------
+// complex helpers
+// ------------------------------------------------------------------------------------------
+IQW_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+IQW_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+IQW_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+IQW_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }          // a * (-i)
+// a * exp(-i*pi/4)  and  a * exp(-3i*pi/4)
+IQW_HD float2 mul_w8_1(float2 a) {
+    const float h = 0.70710678118654752440f;
+    return make_float2((a.x + a.y) * h, (a.y - a.x) * h);
+}
+IQW_HD float2 mul_w8_3(float2 a) {
+    const float h = 0.70710678118654752440f;
+    return make_float2((a.y - a.x) * h, -(a.x + a.y) * h);
+}
+
+// ------------------------------------------------------------------------------------------
+// in-register forward DFTs; element n lives at a[n*S]; outputs in natural order
+// ------------------------------------------------------------------------------------------
+template <int S>
+IQW_HD void bfly2(float2* a) {
+    float2 t = a[S];
+    a[S] = csub(a[0], t);
+    a[0] = cadd(a[0], t);
+}
+
+template <int S>
+IQW_HD void bfly4(float2* a) {
+    float2 t0 = cadd(a[0], a[2 * S]);
+    float2 t1 = csub(a[0], a[2 * S]);
+    float2 t2 = cadd(a[S], a[3 * S]);
+    float2 t3 = mul_mi(csub(a[S], a[3 * S]));
+    a[0] = cadd(t0, t2);
+    a[S] = cadd(t1, t3);
+    a[2 * S] = csub(t0, t2);
+    a[3 * S] = csub(t1, t3);
+}
+
+template <int S>
+IQW_HD void bfly8(float2* a) {
+    // decimation in frequency: X[2k] = DFT4(a_n + a_{n+4}), X[2k+1] = DFT4((a_n - a_{n+4}) W8^n)
+    float2 s0 = cadd(a[0], a[4 * S]), d0 = csub(a[0], a[4 * S]);
+    float2 s1 = cadd(a[S], a[5 * S]), d1 = mul_w8_1(csub(a[S], a[5 * S]));
+    float2 s2 = cadd(a[2 * S], a[6 * S]), d2 = mul_mi(csub(a[2 * S], a[6 * S]));
+    float2 s3 = cadd(a[3 * S], a[7 * S]), d3 = mul_w8_3(csub(a[3 * S], a[7 * S]));
+    float2 e[4] = {s0, s1, s2, s3};
+    float2 o[4] = {d0, d1, d2, d3};
+    bfly4<1>(e);
+    bfly4<1>(o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[(2 * k) * S] = e[k];
+        a[(2 * k + 1) * S] = o[k];
+    }
+}
+
+template <int S>
+IQW_HD void bfly16(float2* a) {
+    // n = 4*n1 + n0, k = k0 + 4*k1:
+    //   y[n0][k0] = sum_n1 a[4 n1 + n0] W4^{n1 k0};  y *= W16^{n0 k0};  X[k0 + 4 k1] = sum_n0 y W4^{n0 k1}
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;   // cos, sin(pi/8)
+    float2 y[16];
+#pragma unroll
+    for (int n0 = 0; n0 < 4; ++n0) {
+        float2 t[4] = {a[n0 * S], a[(n0 + 4) * S], a[(n0 + 8) * S], a[(n0 + 12) * S]};
+        bfly4<1>(t);
+#pragma unroll
+        for (int k0 = 0; k0 < 4; ++k0) y[n0 * 4 + k0] = t[k0];
+    }
+    // W16^m = exp(-2 pi i m / 16)
+    y[1 * 4 + 1] = cmul(y[1 * 4 + 1], make_float2(c1, -s1));     // m = 1
+    y[1 * 4 + 2] = mul_w8_1(y[1 * 4 + 2]);                       // m = 2
+    y[1 * 4 + 3] = cmul(y[1 * 4 + 3], make_float2(s1, -c1));     // m = 3
+    y[2 * 4 + 1] = mul_w8_1(y[2 * 4 + 1]);                       // m = 2
+    y[2 * 4 + 2] = mul_mi(y[2 * 4 + 2]);                         // m = 4
+    y[2 * 4 + 3] = mul_w8_3(y[2 * 4 + 3]);                       // m = 6
+    y[3 * 4 + 1] = cmul(y[3 * 4 + 1], make_float2(s1, -c1));     // m = 3
+    y[3 * 4 + 2] = mul_w8_3(y[3 * 4 + 2]);                       // m = 6
+    y[3 * 4 + 3] = cmul(y[3 * 4 + 3], make_float2(-c1, s1));     // m = 9
+#pragma unroll
+    for (int k0 = 0; k0 < 4; ++k0) {
+        float2 t[4] = {y[0 * 4 + k0], y[1 * 4 + k0], y[2 * 4 + k0], y[3 * 4 + k0]};
+        bfly4<1>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) a[(k0 + 4 * k1) * S] = t[k1];
+    }
+}
+
+template <int R, int S>
+IQW_HD void bfly(float2* a) {
+    if constexpr (R == 2) bfly2<S>(a);
+    else if constexpr (R == 4) bfly4<S>(a);
+    else if constexpr (R == 8) bfly8<S>(a);
+    else bfly16<S>(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// one pass for one thread.  The thread owns butterflies j = ltid + q*TPF, q = 0..E/R-1, and keeps
+// element r of butterfly q in v[q*R + r].
+//   FIRST: v was filled by the caller from global memory (windowed samples), no twiddle
+//   LAST : v is left in registers for the caller's epilogue; bin of v[q*R + r] is j + r*N/R
+// `src`/`dst` are this frame's ping-pong exchange buffers (padded), `tw` the whole twiddle table.
+// ------------------------------------------------------------------------------------------
+template <int LOG2N, int P>
+IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* tw, int ltid) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int E = plan_elems(LOG2N);
+    constexpr int TPF = N / E;
+    constexpr int R = plan_radix(LOG2N, P);
+    constexpr int Ns = plan_ns(LOG2N, P);
+    constexpr int NB = E / R;
+    constexpr bool FIRST = (P == 0);
+    constexpr bool LAST = (P == plan_passes(LOG2N) - 1);
+    constexpr int TWO = plan_tw_offset(LOG2N, P);
+
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int j = ltid + q * TPF;
+        float2* a = v + q * R;
+        if constexpr (!FIRST) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if constexpr ((N / R) % 16 == 0)    // keep the r-offset a compile-time immediate
+                    a[r] = src[pad_index(j) + pad_index(r * (N / R))];
+                else
+                    a[r] = src[pad_index(j + r * (N / R))];
+            }
+            const int i = j & (Ns - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], tw[TWO + (r - 1) * Ns + i]);
+        }
+        bfly<R, 1>(a);
+        if constexpr (!LAST) {
+            const int base = (j / Ns) * (Ns * R) + (j & (Ns - 1));
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if constexpr (Ns % 16 == 0)
+                    dst[pad_index(base) + pad_index(r * Ns)] = a[r];
+                else
+                    dst[pad_index(base + r * Ns)] = a[r];
+            }
+        }
+    }
+}
+
+}  // namespace iqw

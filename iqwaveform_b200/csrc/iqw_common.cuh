@@ -1,0 +1,55 @@
+// iqw_common.cuh -- error plumbing and small device helpers shared by the three kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include "../../include/iqw_b200.h"
+
+namespace iqw {
+
+char* last_error_buffer();   // thread-local, defined in iqw_abi.cu
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define IQW_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::iqw::fail(IQW_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+int device_sm_count(int* sms);
+
+// order-preserving map float32 -> uint32 (total order: -nan < -inf < ... < -0 < +0 < ... < +inf < nan)
+__host__ __device__ __forceinline__ uint32_t float_to_key(float f) {
+#if defined(__CUDA_ARCH__)
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+    return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t b = k ^ ((k & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu);
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+
+// 10*log10(p + eps) in float32, same operation order as the reference's generic branch
+// (power_analysis.py:199-204: abs, += eps, log10, *= 10).
+__device__ __forceinline__ float power_to_dB(float p, float eps) {
+    return 10.0f * log10f(fabsf(p) + eps);
+}
+
+}  // namespace iqw

@@ -1,0 +1,280 @@
+// iqw_stft.cu -- kernel 1: fused overlapped-frame gather * window -> FFT -> |X|^2 / dB -> trim.
+//
+// One pass over the samples replaces the reference's five materialising steps
+// (/root/reference/src/iqwaveform/):
+//   fourier.py:568-581   sliding_window_view + multiply   (writes (T, nfft) complex64)
+//   fourier.py:1044      fft (scipy.fft / cuFFT), in place
+//   power_analysis.py:254-255   abs, square                (writes (T, nfft) float32)
+//   power_analysis.py:199-204   abs, += eps, log10, *= 10  (4 passes)
+//   fourier.py:1295      band slice
+//
+// Work decomposition: a CTA owns FPC frame slots of TPF = nfft/E threads each; thread `ltid` of a
+// slot holds E = 16 (8 for nfft 32/64) complex values in registers.  A persistent grid walks a
+// contiguous range of frame groups per CTA so that the overlapped half of consecutive frames is
+// re-read from L1/L2, never from HBM.  Between passes the values are exchanged through padded
+// ping-pong shared-memory buffers; the per-pass twiddle tables live in shared memory, laid out
+// [r][i] so that a warp reads consecutive entries.
+#include <mutex>
+#include <map>
+#include <utility>
+#include "iqw_common.cuh"
+#include "fft_core.cuh"
+
+namespace iqw {
+
+struct StftArgs {
+    const float2* x;
+    long long n_samples, x_ch_stride;
+    int n_channels;
+    const float* window;
+    const float2* twiddle;
+    long long hop, n_frames;
+    float eps;
+    int bin_lo, bin_hi;
+    void* out;
+    long long out_ch_stride;
+    long long n_groups;        // n_channels * groups_per_channel
+    long long groups_per_ch;   // ceil(n_frames / FPC)
+};
+
+template <int LOG2N>
+struct StftCfg {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int E = plan_elems(LOG2N);
+    static constexpr int TPF = N / E;                           // threads per frame
+    static constexpr int THREADS = TPF >= 256 ? TPF : 256;
+    static constexpr int FPC = THREADS / TPF;                   // frames per CTA iteration
+    static constexpr int NP = plan_passes(LOG2N);
+    static constexpr int TW = plan_tw_size(LOG2N);
+    static constexpr int TW_ALLOC = (TW + 15) & ~15;
+    static constexpr int PADN = padded_size(N);
+    static constexpr int NBUF = NP > 1 ? 2 : 0;
+    static constexpr size_t SMEM = sizeof(float2) * ((size_t)TW_ALLOC + (size_t)NBUF * FPC * PADN);
+    // CTAs per SM we aim for (register budget = 65536 / (THREADS * MIN_BLOCKS))
+    static constexpr int MIN_BLOCKS = THREADS >= 512 ? 1 : 2;
+};
+
+template <int LOG2N, int P>
+struct PassLoop {
+    // runs passes P..NP-1; `par` selects the ping-pong buffer the NEXT exchange writes
+    static __device__ __forceinline__ void run(float2* v, float2* bufs, const float2* tw, int ltid,
+                                               int slot, int& par) {
+        using C = StftCfg<LOG2N>;
+        constexpr bool LAST = (P == C::NP - 1);
+        float2* wr = bufs + ((size_t)par * C::FPC + slot) * C::PADN;
+        const float2* rd = bufs + ((size_t)(par ^ 1) * C::FPC + slot) * C::PADN;
+        fft_pass<LOG2N, P>(v, rd, wr, tw, ltid);
+        if constexpr (!LAST) {
+            __syncthreads();
+            par ^= 1;
+            PassLoop<LOG2N, P + 1>::run(v, bufs, tw, ltid, slot, par);
+        }
+    }
+};
+
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(StftCfg<LOG2N>::THREADS, StftCfg<LOG2N>::MIN_BLOCKS)
+stft_kernel(const StftArgs a) {
+    using C = StftCfg<LOG2N>;
+    constexpr int N = C::N, E = C::E, TPF = C::TPF, FPC = C::FPC;
+    constexpr int R0 = plan_radix(LOG2N, 0);
+    constexpr int RL = plan_radix(LOG2N, C::NP - 1);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    float2* bufs = tw + C::TW_ALLOC;
+
+    for (int i = threadIdx.x; i < C::TW; i += C::THREADS) tw[i] = a.twiddle[i];
+
+    const int slot = threadIdx.x / TPF;
+    const int ltid = threadIdx.x % TPF;
+
+    // window coefficients of the samples this thread loads, kept in registers for every frame
+    float w[E];
+#pragma unroll
+    for (int q = 0; q < E / R0; ++q)
+#pragma unroll
+        for (int r = 0; r < R0; ++r) w[q * R0 + r] = __ldg(a.window + (ltid + q * TPF) + r * (N / R0));
+
+    __syncthreads();
+
+    // contiguous range of frame groups for this CTA
+    const long long per = (a.n_groups + gridDim.x - 1) / gridDim.x;
+    const long long g_begin = per * blockIdx.x;
+    const long long g_end = g_begin + per < a.n_groups ? g_begin + per : a.n_groups;
+    const int nbins = a.bin_hi - a.bin_lo;
+    int par = 0;
+
+    for (long long g = g_begin; g < g_end; ++g) {
+        const long long c = g / a.groups_per_ch;
+        const long long frame = (g - c * a.groups_per_ch) * FPC + slot;
+        const bool valid = frame < a.n_frames;
+
+        float2 v[E];
+        if (valid) {
+            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
+#pragma unroll
+            for (int q = 0; q < E / R0; ++q)
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+                    float2 s = __ldg(src + q * TPF + r * (N / R0));
+                    v[q * R0 + r] = make_float2(s.x * w[q * R0 + r], s.y * w[q * R0 + r]);
+                }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = make_float2(0.f, 0.f);
+        }
+
+        PassLoop<LOG2N, 0>::run(v, bufs, tw, ltid, slot, par);
+
+        if (valid) {
+            const long long row = c * a.out_ch_stride + frame * (long long)nbins - a.bin_lo;
+#pragma unroll
+            for (int q = 0; q < E / RL; ++q)
+#pragma unroll
+                for (int r = 0; r < RL; ++r) {
+                    const int k = (ltid + q * TPF) + r * (N / RL);
+                    if (k >= a.bin_lo && k < a.bin_hi) {
+                        const float2 X = v[q * RL + r];
+                        if constexpr (MODE == IQW_STFT_COMPLEX) {
+                            __stcs(reinterpret_cast<float2*>(a.out) + row + k, X);
+                        } else {
+                            float p = X.x * X.x + X.y * X.y;
+                            if constexpr (MODE == IQW_STFT_DB) p = power_to_dB(p, a.eps);
+                            __stcs(reinterpret_cast<float*>(a.out) + row + k, p);
+                        }
+                    }
+                }
+        }
+        // no trailing barrier needed: the ping-pong parity keeps an exchange buffer from being
+        // rewritten before every thread has passed the barrier that follows its last read
+        if constexpr (C::NP == 1) { /* no shared memory exchange at all */ }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// twiddle tables: one immutable table per (device, log2 nfft), built on first use in float64
+// ---------------------------------------------------------------------------------------------
+__global__ void twiddle_init_kernel(float2* tw, int log2n) {
+    const int np = plan_passes(log2n);
+    for (int p = 1; p < np; ++p) {
+        const int R = plan_radix(log2n, p), Ns = plan_ns(log2n, p), off = plan_tw_offset(log2n, p);
+        const int count = (R - 1) * Ns;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+            const int r = e / Ns + 1, i = e % Ns;
+            double s, c;
+            sincospi(-2.0 * (double)(r * i) / (double)(Ns * R), &s, &c);
+            tw[off + e] = make_float2((float)c, (float)s);
+        }
+    }
+}
+
+static std::mutex g_tw_mutex;
+static std::map<std::pair<int, int>, float2*> g_tw_cache;
+
+static int get_twiddles(int log2n, cudaStream_t stream, const float2** out) {
+    int dev = 0;
+    IQW_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto key = std::make_pair(dev, log2n);
+    auto it = g_tw_cache.find(key);
+    if (it == g_tw_cache.end()) {
+        float2* d = nullptr;
+        const int n = plan_tw_size(log2n) + 16;
+        IQW_CUDA_OK(cudaMalloc(&d, sizeof(float2) * n));
+        twiddle_init_kernel<<<8, 256, 0, stream>>>(d, log2n);
+        IQW_CUDA_OK(cudaGetLastError());
+        IQW_CUDA_OK(cudaStreamSynchronize(stream));   // one-time: visible to every later stream
+        it = g_tw_cache.emplace(key, d).first;
+    }
+    *out = it->second;
+    return IQW_OK;
+}
+
+template <int LOG2N, int MODE>
+static int launch_stft(StftArgs a, cudaStream_t stream) {
+    using C = StftCfg<LOG2N>;
+    auto kern = stft_kernel<LOG2N, MODE>;
+    IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    int sms = 0, per_sm = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    IQW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM));
+    if (per_sm < 1) return fail(IQW_ERR_CUDA, "stft kernel nfft=%d does not fit on an SM", C::N);
+    a.groups_per_ch = (a.n_frames + C::FPC - 1) / C::FPC;
+    a.n_groups = a.groups_per_ch * a.n_channels;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.n_groups) grid = a.n_groups;
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(a);
+    IQW_CUDA_OK(cudaGetLastError());
+    return IQW_OK;
+}
+
+template <int LOG2N>
+static int launch_stft_mode(const StftArgs& a, int mode, cudaStream_t s) {
+    switch (mode) {
+        case IQW_STFT_COMPLEX: return launch_stft<LOG2N, IQW_STFT_COMPLEX>(a, s);
+        case IQW_STFT_POWER: return launch_stft<LOG2N, IQW_STFT_POWER>(a, s);
+        case IQW_STFT_DB: return launch_stft<LOG2N, IQW_STFT_DB>(a, s);
+    }
+    return fail(IQW_ERR_INVALID, "unknown stft mode %d", mode);
+}
+
+}  // namespace iqw
+
+using namespace iqw;
+
+extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples,
+                            int64_t x_channel_stride, const float* d_window, int32_t nfft,
+                            int64_t hop, int64_t n_frames, int32_t mode, float eps, int32_t bin_lo,
+                            int32_t bin_hi, void* d_out, int64_t out_channel_stride, void* stream) {
+    if (!d_x || !d_window || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
+    if (nfft < 2 || (nfft & (nfft - 1)))
+        return fail(IQW_ERR_UNSUPPORTED, "nfft=%d: only powers of two are built", nfft);
+    int log2n = 0;
+    while ((1 << log2n) < nfft) ++log2n;
+    if (log2n < 4 || log2n > 13)
+        return fail(IQW_ERR_UNSUPPORTED, "nfft=%d outside the built range 16..8192", nfft);
+    if (hop < 1) return fail(IQW_ERR_INVALID, "hop=%lld must be >= 1", (long long)hop);
+    if (n_channels < 0 || n_frames < 0) return fail(IQW_ERR_INVALID, "negative size");
+    if (n_channels == 0 || n_frames == 0) return IQW_OK;
+    if ((n_frames - 1) * hop + nfft > n_samples)
+        return fail(IQW_ERR_INVALID, "n_frames=%lld does not fit in n_samples=%lld",
+                    (long long)n_frames, (long long)n_samples);
+    if (bin_lo < 0 || bin_hi > nfft || bin_lo >= bin_hi)
+        return fail(IQW_ERR_INVALID, "bad bin range [%d, %d)", bin_lo, bin_hi);
+    if (x_channel_stride < n_samples && n_channels > 1)
+        return fail(IQW_ERR_INVALID, "x_channel_stride smaller than n_samples");
+    if (out_channel_stride < n_frames * (int64_t)(bin_hi - bin_lo) && n_channels > 1)
+        return fail(IQW_ERR_INVALID, "out_channel_stride too small");
+    if (n_channels > 0x7fffffff) return fail(IQW_ERR_INVALID, "too many channels");
+
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StftArgs a{};
+    a.x = static_cast<const float2*>(d_x);
+    a.n_samples = n_samples;
+    a.x_ch_stride = x_channel_stride;
+    a.n_channels = (int)n_channels;
+    a.window = d_window;
+    a.hop = hop;
+    a.n_frames = n_frames;
+    a.eps = eps;
+    a.bin_lo = bin_lo;
+    a.bin_hi = bin_hi;
+    a.out = d_out;
+    a.out_ch_stride = out_channel_stride;
+    if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;
+
+    switch (log2n) {
+        case 4: return launch_stft_mode<4>(a, mode, s);
+        case 5: return launch_stft_mode<5>(a, mode, s);
+        case 6: return launch_stft_mode<6>(a, mode, s);
+        case 7: return launch_stft_mode<7>(a, mode, s);
+        case 8: return launch_stft_mode<8>(a, mode, s);
+        case 9: return launch_stft_mode<9>(a, mode, s);
+        case 10: return launch_stft_mode<10>(a, mode, s);
+        case 11: return launch_stft_mode<11>(a, mode, s);
+        case 12: return launch_stft_mode<12>(a, mode, s);
+        case 13: return launch_stft_mode<13>(a, mode, s);
+    }
+    return fail(IQW_ERR_UNSUPPORTED, "nfft=%d", nfft);
+}

@@ -1,0 +1,227 @@
+"""B200-native ``stft`` / ``spectrogram`` / ``persistence_spectrum`` with the reference signatures.
+
+Mirrors /root/reference/src/iqwaveform/fourier.py:927-1057 (stft), 1203-1233 (spectrogram) and
+1236-1327 (power_spectral_density == the north-star's persistence_spectrum).  The host side does
+what the reference does on the host for every backend (parameter validation, window design, axis
+arrays, band edges); all sample-rate work runs in the CUDA library behind include/iqw_b200.h.
+
+Deliberate differences from what the reference *returns* (SURVEY.md section 0):
+* quantile rows of ``power_spectral_density`` hold the values the reference computes and then
+  loses (``fourier.py:1319-1320`` writes them into a temporary copy);
+* overlapped ``stft`` works for any ``axis`` (the reference only for the last axis), and 1-D input
+  to ``power_spectral_density`` works; the output layout is the one the reference produces
+  wherever the reference works.
+* ``spectrogram`` takes two additive keyword arguments, ``dB=`` and ``eps=``, fusing the
+  ``powtodB(spectrogram(...))`` composition the reference's callers use (``figures.py:486``).
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _arrays, _lib, _plan
+from ._plan import INF
+
+__all__ = ['stft', 'spectrogram', 'power_spectral_density', 'persistence_spectrum', 'fftfreq',
+           'get_window', 'equivalent_noise_bandwidth']
+
+fftfreq = _plan.fftfreq
+
+_window_cache: dict = {}
+_window_lock = threading.Lock()
+
+
+def get_window(name_or_tuple, nwindow: int, nzero: int = 0, *, norm: bool = True,
+               fftshift: bool = False) -> np.ndarray:
+    """host window design (fourier.py:70-157), float32"""
+    w = _plan.design_window(_plan.window_key(name_or_tuple), nwindow, nzero, norm=norm)
+    if not fftshift:
+        w = w.copy()
+        w[1::2] *= -1.0
+    return w
+
+
+def equivalent_noise_bandwidth(window, N: int) -> float:
+    """fourier.py:272-286: ENBW in bins"""
+    return float(_plan._enbw(_plan.window_key(window), N))
+
+
+def _device_window(window, nfft: int, nzero: int, norm, hop: int, device) -> torch.Tensor:
+    key = (_plan.window_key(window), nfft, nzero, norm, hop, device.index)
+    with _window_lock:
+        w = _window_cache.get(key)
+        if w is None:
+            c = _plan.stft_coefficients(key[0], nfft, nzero, norm, hop)
+            w = torch.from_numpy(c).to(device)
+            _window_cache[key] = w
+    return w
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _frame_count(n: int, nfft: int, noverlap: int, truncate: bool) -> int:
+    if noverlap == 0:
+        if n % nfft and not truncate:
+            raise ValueError(f'axis 0 size {n} is not a factor of block size {nfft}')
+        return n // nfft
+    # overlap path: the partial tail frame is dropped whatever `truncate` says (fourier.py:568-569)
+    if n < nfft:
+        raise ValueError('window shape cannot be larger than input array shape')
+    return (n - nfft) // (nfft - noverlap) + 1
+
+
+def _check_window_arg(window):
+    if window is None or isinstance(window, str):
+        return
+    if isinstance(window, (tuple, list)) and len(window) and isinstance(window[0], str):
+        return
+    raise NotImplementedError(
+        'array-valued windows are not built (they raise UnboundLocalError in the reference, '
+        'fourier.py:1012)')
+
+
+def _stft_device(x2: torch.Tensor, *, window, nfft: int, noverlap: int, nzero: int, norm,
+                 truncate: bool, mode: int, eps: float = 0.0, bin_lo: int = 0, bin_hi=None,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+    """(C, N) complex64 on the device -> (C, T, nbins)"""
+    if x2.dtype != torch.complex64:
+        raise NotImplementedError(f'only complex64 waveforms are built (got {x2.dtype})')
+    if nfft < 1 or not 0 <= noverlap < nfft:
+        raise ValueError('need 0 <= noverlap < nperseg')
+    C, N = x2.shape
+    if x2.numel() == 0:
+        raise IndexError('cannot form blocks on arrays of size 0')
+    hop = nfft - noverlap
+    T = _frame_count(N, nfft, noverlap, truncate)
+    bin_hi = nfft if bin_hi is None else bin_hi
+    nb = bin_hi - bin_lo
+    w = _device_window(window, nfft, nzero, norm, hop, x2.device)
+    dtype = torch.complex64 if mode == _lib.STFT_COMPLEX else torch.float32
+    if out is None:
+        out = torch.empty((C, T, nb), dtype=dtype, device=x2.device)
+    elif out.shape != (C, T, nb) or out.dtype != dtype or not out.is_contiguous():
+        raise ValueError(f'out must be a contiguous {dtype} tensor of shape {(C, T, nb)}')
+    if T == 0 or C == 0:
+        return out
+    _lib.check(_lib.lib.iqw_stft_c64(
+        ctypes.c_void_p(x2.data_ptr()), C, N, x2.stride(0) if C > 1 else N,
+        ctypes.c_void_p(w.data_ptr()), nfft, hop, T, mode, eps, bin_lo, bin_hi,
+        ctypes.c_void_p(out.data_ptr()), T * nb, _stream_ptr(x2.device)))
+    return out
+
+
+def stft(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, nzero: int = 0,
+         axis: int = 0, truncate: bool = True, norm: str | None = None, overwrite_x=False,
+         return_axis_arrays=True, out=None):
+    """short-time Fourier transform; same arguments and return value as the reference
+    (fourier.py:927-1057).  Output index k is frequency index k - nfft/2 (no fftshift needed)."""
+    if norm not in ('power', None):
+        raise TypeError('norm must be "power" or None')
+    _check_window_arg(window)
+    xd, res = _arrays.to_device(x)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+    y = _stft_device(x2, window=window, nfft=int(nperseg), noverlap=int(noverlap), nzero=int(nzero),
+                     norm=norm, truncate=truncate, mode=_lib.STFT_COMPLEX,
+                     out=out if (out is not None and not trail) else None)
+    y = res.give_back(_arrays.restore_layout(y, lead, trail, 2))
+    if not return_axis_arrays:
+        return y
+    ax = axis if axis >= 0 else axis + xd.ndim
+    freqs, times = _plan.stft_axes(fs, int(nperseg), y.shape[ax], noverlap / nperseg)
+    return freqs, times, y
+
+
+def spectrogram(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, nzero: int = 0,
+                axis: int = 0, truncate: bool = True, return_axis_arrays: bool = True,
+                dB: bool = False, eps: float = 0.0):
+    """power spectrogram (fourier.py:1203-1233); with ``dB=True`` the fused
+    ``10*log10(power + eps)`` of power_analysis.py:168-206"""
+    _check_window_arg(window)
+    xd, res = _arrays.to_device(x)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+    p = _stft_device(x2, window=window, nfft=int(nperseg), noverlap=int(noverlap), nzero=int(nzero),
+                     norm='power', truncate=truncate,
+                     mode=_lib.STFT_DB if dB else _lib.STFT_POWER, eps=float(eps))
+    p = res.give_back(_arrays.restore_layout(p, lead, trail, 2))
+    if not return_axis_arrays:
+        return p
+    ax = axis if axis >= 0 else axis + xd.ndim
+    freqs, times = _plan.stft_axes(fs, int(nperseg), p.shape[ax], noverlap / nperseg)
+    return freqs, times, p
+
+
+def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """statistics over axis 1 of a (C, T, nbins) float32 device tensor -> (C, nstat, nbins).
+    The device-side part of fourier.py:1311-1325."""
+    if p.dtype != torch.float32 or p.ndim != 3:
+        raise ValueError('expected a (channels, frames, bins) float32 tensor')
+    if not p.is_contiguous():
+        p = p.contiguous()
+    C, T, nb = p.shape
+    if T < 1:
+        raise ValueError('cannot take statistics over zero frames')
+    reqs = _plan.stat_requests(list(statistics), T)
+    if out is None:
+        out = torch.empty((C, len(reqs), nb), dtype=torch.float32, device=p.device)
+    ws_bytes = _lib.lib.iqw_time_stats_workspace_bytes(C, T, nb, len(reqs))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
+    groups = _plan.split_requests(reqs, T)
+    for g in groups:
+        arr = (_lib.iqw_stat * len(g))(*[reqs[i] for i in g])
+        sub = out if len(groups) == 1 else torch.empty((C, len(g), nb), dtype=torch.float32,
+                                                       device=p.device)
+        _lib.check(_lib.lib.iqw_time_stats_f32(
+            ctypes.c_void_p(p.data_ptr()), C, T, nb, T * nb, arr, len(g), int(bool(dB)), eps,
+            ctypes.c_void_p(sub.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws_bytes,
+            _stream_ptr(p.device)))
+        if sub is not out:
+            out[:, g, :] = sub
+    return out
+
+
+def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: float,
+                           fractional_overlap=0, fractional_window: float = 1, statistics,
+                           truncate=True, dB=True, axis=0):
+    """persistence spectrum: per-bin statistics over time of the (dB) power spectrogram.
+    Same arguments as the reference (fourier.py:1236-1327); returns (channels, nstat, nbins)
+    float32 for (channels, time) input with axis=1, (nstat, nbins) for 1-D input."""
+    if _plan.isroundmod(fs, resolution):
+        nfft = round(fs / resolution)
+        noverlap = round(fractional_overlap * nfft)
+    else:
+        raise ValueError('sample_rate_Hz/resolution must be a counting number')
+    if _plan.isroundmod((1 - fractional_window) * nfft, 1):
+        nzero = round((1 - fractional_window) * nfft)
+    else:
+        raise ValueError(
+            '(1-fractional_window) * (sample_rate/frequency_resolution) must be a counting number')
+    _check_window_arg(window)
+    statistics = list(statistics)
+    _plan.stat_requests(statistics, 2)          # validates names before any device work
+
+    xd, res = _arrays.to_device(x)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+
+    bin_lo, bin_hi = 0, nfft
+    if truncate and bandwidth != INF:
+        bin_lo, bin_hi = _plan.freq_band_edges(nfft, 1.0 / fs, -bandwidth / 2, +bandwidth / 2)
+
+    C = x2.shape[0]
+    out = torch.empty((C, len(statistics), bin_hi - bin_lo), dtype=torch.float32, device=x2.device)
+    scratch = None
+    for c in range(C):      # one channel's spectrogram in flight at a time (8 GB at config 3)
+        p = _stft_device(x2[c:c + 1], window=window, nfft=nfft, noverlap=noverlap, nzero=nzero,
+                         norm='power', truncate=True, mode=_lib.STFT_POWER, bin_lo=bin_lo,
+                         bin_hi=bin_hi, out=scratch)
+        scratch = p
+        time_statistics(p, statistics, dB=bool(dB), eps=1e-25, out=out[c:c + 1])
+    return res.give_back(_arrays.restore_layout(out, lead, trail, 2))
+
+
+persistence_spectrum = power_spectral_density

@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY -- import the unmodified reference (dgkuester/iqwaveform 0.52.0).
+
+The reference cannot be imported as-is in this image: five third-party
+modules are absent and one private SciPy symbol has disappeared.  This module installs the
+smallest set of stand-ins that lets ``import iqwaveform`` run WITHOUT editing reference code:
+
+* ``array_api_compat``      -> the real vendored copy in ``sklearn.externals`` (authentic dispatch)
+* ``numexpr``               -> stub whose ``evaluate`` raises (ndarrays never reach it, fact 0.5)
+* ``xarray``/``methodtools``-> empty stand-ins (never touched on the hot path)
+* ``scipy.signal.windows._windows._win_equiv`` -> ``{}`` when missing (``windows.py:119``)
+
+``/root/reference`` exists only in the build container; ``load()`` returns ``None`` elsewhere and
+nothing that runs on the GPU box may depend on it.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.machinery
+import os
+import sys
+import types
+
+REFERENCE_SRC = '/root/reference/src'
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_SRC, 'iqwaveform'))
+
+
+def _stub(name: str, **attrs):
+    if name in sys.modules:
+        return
+    m = types.ModuleType(name)
+    # util.lazy_import() calls importlib.util.find_spec, which needs a __spec__
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+
+
+def load():
+    """return the reference package (module ``iqwaveform``) or None when it is not present"""
+    if not available():
+        return None
+    if 'iqwaveform' in sys.modules:
+        return sys.modules['iqwaveform']
+
+    try:
+        import array_api_compat  # noqa: F401
+    except ImportError:
+        import sklearn.externals.array_api_compat as aac
+        import sklearn.externals.array_api_compat.numpy as aacnp
+
+        sys.modules['array_api_compat'] = aac
+        sys.modules['array_api_compat.numpy'] = aacnp
+
+    def _never(*a, **k):
+        raise RuntimeError('numexpr stub reached (only python scalars get here)')
+
+    for name, attrs in (
+        ('numexpr', dict(evaluate=_never)),
+        ('xarray', dict(DataArray=type('DataArray', (), {}))),
+        ('methodtools', dict(lru_cache=lambda *a, **k: (lambda f: f))),
+    ):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            _stub(name, **attrs)
+
+    import scipy.signal.windows._windows as _w
+
+    if not hasattr(_w, '_win_equiv'):
+        _w._win_equiv = {}
+
+    if REFERENCE_SRC not in sys.path:
+        sys.path.insert(0, REFERENCE_SRC)
+    return importlib.import_module('iqwaveform')
