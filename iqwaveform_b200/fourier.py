@@ -75,6 +75,25 @@ def _frame_count(n: int, nfft: int, noverlap: int, truncate: bool) -> int:
     return (n - nfft) // (nfft - noverlap) + 1
 
 
+def _host_checks(x, axis: int, nfft: int, noverlap: int, truncate: bool) -> None:
+    """the reference's shape errors, raised before any byte moves to the device"""
+    shape = getattr(x, 'shape', None)
+    if shape is None:
+        raise TypeError('unrecognized object type')
+    ndim = len(shape)
+    ax = axis + ndim if axis < 0 else axis
+    if not 0 <= ax < ndim:
+        raise ValueError(f'axis {axis} exceeds the number of dimensions')
+    size = 1
+    for d in shape:
+        size *= d
+    if size == 0:
+        raise IndexError('cannot form blocks on arrays of size 0')
+    if nfft < 1 or not 0 <= noverlap < nfft:
+        raise ValueError('need 0 <= noverlap < nperseg')
+    _frame_count(shape[ax], nfft, noverlap, truncate)
+
+
 def _check_window_arg(window):
     if window is None or isinstance(window, str):
         return
@@ -123,6 +142,7 @@ def stft(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, nzero: 
     if norm not in ('power', None):
         raise TypeError('norm must be "power" or None')
     _check_window_arg(window)
+    _host_checks(x, axis, int(nperseg), int(noverlap), truncate)
     xd, res = _arrays.to_device(x)
     x2, lead, trail = _arrays.as_channels(xd, axis)
     y = _stft_device(x2, window=window, nfft=int(nperseg), noverlap=int(noverlap), nzero=int(nzero),
@@ -204,6 +224,7 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
     _check_window_arg(window)
     statistics = list(statistics)
     _plan.stat_requests(statistics, 2)          # validates names before any device work
+    _host_checks(x, axis, nfft, noverlap, True)
 
     xd, res = _arrays.to_device(x)
     x2, lead, trail = _arrays.as_channels(xd, axis)

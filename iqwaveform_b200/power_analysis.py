@@ -37,15 +37,24 @@ def iq_to_bin_power(iq, Ts: float, Tbin: float, randomize: bool = False, kind='m
     elif not isinstance(kind, Number):
         raise ValueError(f'invalid statistic ufunc "{kind}"')
 
+    shape = getattr(iq, 'shape', None)
+    if shape is None:
+        raise TypeError('unrecognized object type')
+    ax = axis + len(shape) if axis < 0 else axis
+    if not 0 <= ax < len(shape):
+        raise ValueError(f'axis {axis} exceeds the number of dimensions')
+    if 0 in tuple(shape):
+        raise IndexError('cannot form blocks on arrays of size 0')
+    if nb < 1:
+        raise ValueError('bin period shorter than one sample')
+    if shape[ax] % nb and not truncate:
+        raise ValueError(f'axis 0 size {shape[ax]} is not a factor of block size {nb}')
+
     xd, res = _arrays.to_device(iq)
     if xd.dtype != torch.complex64:
         raise NotImplementedError(f'only complex64 waveforms are built (got {xd.dtype})')
-    if xd.numel() == 0:
-        raise IndexError('cannot form blocks on arrays of size 0')
     x2, lead, trail = _arrays.as_channels(xd, axis)
     C, N = x2.shape
-    if N % nb and not truncate:
-        raise ValueError(f'axis 0 size {N} is not a factor of block size {nb}')
     n_bins = N // nb
     dev = x2.device
     ch_stride = x2.stride(0) if C > 1 else N

@@ -1,0 +1,307 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the numpy oracle on identical seeded
+inputs and against the committed golden fixtures (outputs of the unmodified reference).
+Tolerances are defined in tests/_tol.py."""
+import numpy as np
+import pytest
+import torch
+
+import _tol
+from conftest import load_golden
+import iqwaveform_b200 as iqw
+from oracle import iqw_oracle as orc
+from oracle.make_golden import synth
+
+pytestmark = pytest.mark.gpu
+
+NFFTS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
+
+
+def dev_of(x, cuda_device):
+    return torch.from_numpy(x).to(cuda_device)
+
+
+# ---------------------------------------------------------------------------------------------
+# stft
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('nfft', NFFTS)
+@pytest.mark.parametrize('overlap', [0.0, 0.5, 0.75])
+def test_stft_vs_oracle(cuda_device, nfft, overlap):
+    nov = int(nfft * overlap)
+    x = synth(nfft + 1, (2, nfft * 23 + 17))             # ragged tail on purpose
+    for norm in ('power', None):
+        f, t, y = orc.stft(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm=norm)
+        f2, t2, y2 = iqw.stft(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft,
+                              noverlap=nov, axis=1, norm=norm)
+        assert isinstance(f2, np.ndarray) and np.array_equal(f, f2) and np.array_equal(t, t2)
+        assert y2.dtype == torch.complex64 and tuple(y2.shape) == y.shape
+        err = np.abs(y2.cpu().numpy() - y) / _tol.complex_tol(y)
+        assert err.max() <= 1.0, (norm, err.max())
+
+
+@pytest.mark.parametrize('name', ['stft_hann_256_128_power', 'stft_hann_256_128_cola',
+                                  'stft_bh_512_0_power', 'stft_kaiser_64_48_power',
+                                  'stft_hann_1024_512_nzero'])
+def test_stft_vs_golden(cuda_device, name):
+    p, a = load_golden(name)
+    f, t, y = iqw.stft(dev_of(a['x'], cuda_device), **p)
+    assert np.array_equal(f, a['freqs']) and np.array_equal(t, a['times'])
+    assert tuple(y.shape) == a['y'].shape
+    assert (np.abs(y.cpu().numpy() - a['y']) / _tol.complex_tol(a['y'])).max() <= 1.0
+
+
+def test_stft_layouts(cuda_device):
+    """1-D axis 0, (C,N) axis 1, (N,C) axis 0 with and without overlap, negative axis"""
+    x = synth(3, (3, 5000))
+    _, _, want = orc.stft(x, fs=1.0, window='hann', nperseg=128, noverlap=64, axis=1, norm='power')
+    xd = dev_of(x, cuda_device)
+    got1 = iqw.stft(xd[0], fs=1.0, window='hann', nperseg=128, noverlap=64, axis=0, norm='power',
+                    return_axis_arrays=False)
+    assert tuple(got1.shape) == want.shape[1:]
+    np.testing.assert_allclose(got1.cpu().numpy(), want[0], atol=2e-7 * np.abs(want).max())
+    got2 = iqw.stft(xd, fs=1.0, window='hann', nperseg=128, noverlap=64, axis=-1, norm='power',
+                    return_axis_arrays=False)
+    np.testing.assert_allclose(got2.cpu().numpy(), want, atol=2e-7 * np.abs(want).max())
+    # time axis first: the reference (noverlap=0) returns (T, nfft, C)
+    _, _, w0 = orc.stft(x, fs=1.0, window='hann', nperseg=128, noverlap=0, axis=1, norm='power')
+    got3 = iqw.stft(xd.T.contiguous(), fs=1.0, window='hann', nperseg=128, noverlap=0, axis=0,
+                    norm='power', return_axis_arrays=False)
+    assert tuple(got3.shape) == (w0.shape[1], 128, 3)
+    np.testing.assert_allclose(got3.cpu().numpy(), np.moveaxis(w0, 0, -1), atol=2e-7 * np.abs(w0).max())
+
+
+def test_known_answers_on_gpu(cuda_device):
+    nfft, hop, n = 64, 16, 1000
+    x = np.arange(n).astype(np.complex64)
+    _, t, y = iqw.stft(dev_of(x, cuda_device), fs=1.0, window='rect', nperseg=nfft,
+                       noverlap=nfft - hop, norm='power')
+    T = (n - nfft) // hop + 1
+    m = np.arange(T)
+    assert tuple(y.shape) == (T, nfft) and np.array_equal(t, m * float(hop))
+    np.testing.assert_allclose(y[:, nfft // 2].real.cpu().numpy(), m * hop + (nfft - 1) / 2, rtol=1e-6)
+    s = 333
+    x = np.zeros(n, np.complex64); x[s] = 1
+    p = iqw.spectrogram(dev_of(x, cuda_device), fs=1.0, window='rect', nperseg=nfft,
+                        noverlap=nfft - hop, return_axis_arrays=False).cpu().numpy()
+    hit = (m * hop <= s) & (s < m * hop + nfft)
+    assert np.all(p[hit].min(axis=1) > 0) and np.all(p[~hit] == 0)
+    k, A = 5, 2.0
+    x = (A * np.exp(2j * np.pi * k * np.arange(n) / nfft)).astype(np.complex64)
+    p = iqw.spectrogram(dev_of(x, cuda_device), fs=1.0, window='rect', nperseg=nfft, noverlap=0,
+                        return_axis_arrays=False).cpu().numpy()
+    assert np.all(p.argmax(axis=1) == k + nfft // 2)
+    np.testing.assert_allclose(p.max(axis=1), A * A, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# spectrogram (power, dB)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('nfft,overlap,window', [(64, 0.75, 'hann'), (256, 0.5, 'hann'),
+                                                 (1024, 0.5, 'hann'), (2048, 0.5, 'blackmanharris'),
+                                                 (4096, 0.5, 'hann'), (8192, 0.75, ('kaiser', 10.0)),
+                                                 (4096, 0.0, 'rect')])
+def test_spectrogram_vs_oracle_and_truth(cuda_device, nfft, overlap, window):
+    nov = int(nfft * overlap)
+    x = synth(7 * nfft, (2, nfft * 30 + 5))
+    _, _, ref = orc.spectrogram(x, fs=1e8, window=window, nperseg=nfft, noverlap=nov, axis=1)
+    truth = orc.stft_power_f64(x, window=window, nperseg=nfft, noverlap=nov)
+    got = iqw.spectrogram(dev_of(x, cuda_device), fs=1e8, window=window, nperseg=nfft,
+                          noverlap=nov, axis=1, return_axis_arrays=False)
+    assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
+    got = got.cpu().numpy()
+    assert _tol.power_err_units(got, ref) <= 1.0
+    # at least as close to the float64 evaluation as the reference is
+    e_gpu, e_ref = _tol.power_err_units(got, truth), _tol.power_err_units(ref, truth)
+    assert e_gpu <= max(1.25 * e_ref, 0.1), (e_gpu, e_ref)
+    # fused dB output == powtodB(spectrogram) of the reference
+    dref = orc.powtodB(ref.copy())
+    dgot = iqw.spectrogram(dev_of(x, cuda_device), fs=1e8, window=window, nperseg=nfft,
+                           noverlap=nov, axis=1, return_axis_arrays=False, dB=True).cpu().numpy()
+    finite = np.isfinite(dref)
+    tol = _tol.db_tol(dref, ref.max(axis=-1, keepdims=True))
+    assert np.all(np.abs(dgot - dref)[finite] <= tol[finite])
+    assert np.array_equal(np.isneginf(dgot), np.isneginf(dref)) or not np.any(~finite)
+
+
+@pytest.mark.parametrize('name', ['spg_bh_2048_1024', 'spg_hann_1024_768', 'spg_rect_4096_0'])
+def test_spectrogram_vs_golden(cuda_device, name):
+    p, a = load_golden(name)
+    f, t, got = iqw.spectrogram(dev_of(a['x'], cuda_device), **p)
+    assert np.array_equal(f, a['freqs']) and np.array_equal(t, a['times'])
+    assert _tol.power_err_units(got.cpu().numpy(), a['power']) <= 1.0
+    _, _, d = iqw.spectrogram(dev_of(a['x'], cuda_device), dB=True, **p)
+    tol = _tol.db_tol(a['dB'], a['power'].max(axis=-1, keepdims=True))
+    assert np.all(np.abs(d.cpu().numpy() - a['dB']) <= tol)
+
+
+def test_zero_input_gives_minus_inf_dB(cuda_device):
+    x = torch.zeros(4096, dtype=torch.complex64, device=cuda_device)
+    d = iqw.spectrogram(x, fs=1.0, window='hann', nperseg=256, return_axis_arrays=False, dB=True)
+    assert torch.all(torch.isneginf(d))           # reference: log10(0) = -inf, silently
+    d = iqw.spectrogram(x, fs=1.0, window='hann', nperseg=256, return_axis_arrays=False, dB=True, eps=1e-25)
+    np.testing.assert_allclose(d.cpu().numpy(), -250.0, atol=1e-4)
+
+
+def test_host_arrays_round_trip(cuda_device):
+    """numpy in -> numpy out, CPU torch in -> CPU torch out (host<->device copies inside)"""
+    x = synth(9, (2, 40000))
+    _, _, ref = orc.spectrogram(x, fs=1e6, window='hann', nperseg=1024, noverlap=512, axis=1)
+    f, t, got = iqw.spectrogram(x, fs=1e6, window='hann', nperseg=1024, noverlap=512, axis=1)
+    assert isinstance(got, np.ndarray) and _tol.power_err_units(got, ref) <= 1.0
+    got = iqw.spectrogram(torch.from_numpy(x), fs=1e6, window='hann', nperseg=1024, noverlap=512,
+                          axis=1, return_axis_arrays=False)
+    assert isinstance(got, torch.Tensor) and not got.is_cuda
+    assert _tol.power_err_units(got.numpy(), ref) <= 1.0
+
+
+def test_unsupported_sizes_fail_loudly(cuda_device):
+    x = torch.zeros(1 << 18, dtype=torch.complex64, device=cuda_device)
+    with pytest.raises(NotImplementedError):
+        iqw.spectrogram(x, fs=1.0, window='hann', nperseg=1000)
+    with pytest.raises(NotImplementedError):
+        iqw.spectrogram(x, fs=1.0, window='hann', nperseg=65536)
+    with pytest.raises(NotImplementedError):
+        iqw.spectrogram(x.to(torch.complex128), fs=1.0, window='hann', nperseg=64)
+
+
+# ---------------------------------------------------------------------------------------------
+# persistence spectrum
+# ---------------------------------------------------------------------------------------------
+def _check_persistence(got, ref, stats, x, nfft, dB, peak):
+    isq = orc.find_float_inds(stats)
+    for i, s in enumerate(stats):
+        g, r = got[:, i].astype(np.float64), ref[:, i].astype(np.float64)
+        if dB:
+            tol = _tol.db_tol(r, peak)
+            if s in ('mean', 'rms'):
+                tol = np.maximum(tol, 1e-3)       # reference's fp32 running sum
+            assert np.all(np.abs(g - r) <= tol), (s, np.max(np.abs(g - r) / tol))
+        else:
+            tol = _tol.POWER_RTOL * np.abs(r) + _tol.POWER_FLOOR * peak
+            if s in ('mean', 'rms'):
+                tol = tol + 2e-5 * np.abs(r)
+            assert np.all(np.abs(g - r) <= tol), (s, np.max(np.abs(g - r) / tol))
+
+
+@pytest.mark.parametrize('n,nfft,ovl,stats,kw', [
+    (1 << 18, 1024, 0.5, [0.5, 0.99, 'mean', 'max'], {}),
+    (1 << 19, 1024, 0.5, [0.1, 0.5, 0.9, 0.999, 'min', 'median', 'rms', 'peak'], {}),
+    (1 << 19, 4096, 0.5, [0.1, 0.5, 0.9, 0.999], dict(bandwidth=0.5e6)),
+    (1 << 16, 256, 0.75, ['mean', 0.25, 'max', 1.0, 0.0], dict(dB=False)),
+    (1 << 17, 512, 0.5, ['0.5', 'max'], dict(fractional_window=0.75)),
+    (1 << 17, 2048, 0.0, [i / 10 for i in range(1, 10)], {}),          # 18 ranks -> split calls
+])
+def test_persistence_vs_oracle(cuda_device, n, nfft, ovl, stats, kw):
+    x = synth(n % 89, (2, n))
+    args = dict(fs=1e6, window='hann', resolution=1e6 / nfft, fractional_overlap=ovl,
+                statistics=stats, axis=1, **kw)
+    ref = orc.persistence_spectrum(x, **args)
+    got = iqw.persistence_spectrum(dev_of(x, cuda_device), **args)
+    assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
+    nz = round((1 - kw.get('fractional_window', 1)) * nfft)
+    _, _, p = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=round(ovl * nfft),
+                              nzero=nz, axis=1)
+    peak = p.max(axis=(1, 2))[:, None]
+    _check_persistence(got.cpu().numpy(), ref, stats, x, nfft, kw.get('dB', True), peak)
+
+
+@pytest.mark.parametrize('name', ['psd_hann_1024_half', 'psd_hann_4096_trim', 'psd_bh_256_linear'])
+def test_persistence_vs_golden(cuda_device, name):
+    p, a = load_golden(name)
+    got = iqw.power_spectral_density(dev_of(a['x'], cuda_device), **p).cpu().numpy()
+    isq = a['is_quantile']
+    ref = np.empty_like(got)
+    ref[:, isq] = a['quantile_rows']
+    ref[:, ~isq] = a['named_rows']
+    nfft = round(p['fs'] / p['resolution'])
+    _, _, pw = orc.spectrogram(a['x'], fs=p['fs'], window=p['window'], nperseg=nfft,
+                               noverlap=round(p['fractional_overlap'] * nfft), axis=1)
+    _check_persistence(got, ref, p['statistics'], a['x'], nfft, p.get('dB', True),
+                       pw.max(axis=(1, 2))[:, None])
+
+
+def test_persistence_1d_and_config1_shape(cuda_device):
+    """BASELINE config 1 at reduced length (the full 1 s runs in bench.py)"""
+    x = synth(21, (1, 1536000))
+    args = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5,
+                statistics=[0.5, 0.99], dB=True)
+    ref = orc.persistence_spectrum(x, axis=1, **args)
+    got = iqw.persistence_spectrum(dev_of(x[0], cuda_device), axis=0, **args)
+    assert tuple(got.shape) == (2, 1024)
+    _, _, p = orc.spectrogram(x, fs=15.36e6, window='hann', nperseg=1024, noverlap=512, axis=1)
+    _check_persistence(got.cpu().numpy()[None], ref, [0.5, 0.99], x, 1024, True, p.max())
+
+
+# ---------------------------------------------------------------------------------------------
+# exact order statistics (no FFT involved): bitwise against numpy
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('T,nb', [(1, 5), (2, 130), (3, 1), (77, 64), (1025, 33), (5000, 300),
+                                  (70001, 257), (300000, 128)])
+def test_time_statistics_bitwise(cuda_device, T, nb):
+    rng = np.random.default_rng(T)
+    a = rng.standard_normal((2, T, nb)).astype(np.float32)
+    a[0, :, 0] = 1.5                                    # constant column
+    if nb > 1:
+        a[0, :, 1] = np.round(a[0, :, 1])               # heavy ties
+    if nb > 2 and T > 10:
+        a[1, 3, 2], a[1, 4, 2] = 1e30, -1e30            # outliers far outside the sampled range
+        a[1, :, 3 % nb] = np.where(np.arange(T) % 2 == 0, 0.0, -0.0)   # signed zeros
+    if nb > 4:
+        a[1, :, 4] = np.exp(6 * a[1, :, 4])             # 50 dB of dynamic range
+        a[0, :, 4] = np.arange(T, dtype=np.float32)     # sorted ramp
+    qs = [0.0, 0.1, 0.5, 0.999, 1.0]
+    got = iqw.time_statistics(dev_of(a, cuda_device), qs + ['median', 'min', 'max', 'mean'],
+                              dB=False).cpu().numpy()
+    want = np.quantile(a, np.array(qs, dtype=np.float32), axis=1)
+    for i in range(len(qs)):
+        assert np.array_equal(got[:, i], want[i]), qs[i]
+    assert np.array_equal(got[:, 5], np.median(a, axis=1))
+    assert np.array_equal(got[:, 6], a.min(axis=1)) and np.array_equal(got[:, 7], a.max(axis=1))
+    truth = a.astype(np.float64).mean(axis=1)
+    np.testing.assert_allclose(got[:, 8], truth, rtol=1e-6, atol=1e-7 * np.abs(a).max())
+
+
+def test_time_statistics_dB_is_monotone_image(cuda_device):
+    rng = np.random.default_rng(2)
+    p = rng.exponential(1e-4, (1, 20000, 96)).astype(np.float32)
+    qs = [0.1, 0.5, 0.9]
+    got = iqw.time_statistics(dev_of(p, cuda_device), qs + ['max', 'min', 'mean'], dB=True,
+                              eps=1e-25).cpu().numpy()
+    d = orc.powtodB(p.copy(), eps=1e-25)
+    want = np.quantile(d, np.array(qs, dtype=np.float32), axis=1)
+    np.testing.assert_allclose(got[:, :3], np.moveaxis(want, 0, 1), atol=5e-5)
+    np.testing.assert_allclose(got[:, 3], d.max(axis=1), atol=5e-5)
+    np.testing.assert_allclose(got[:, 4], d.min(axis=1), atol=5e-5)
+    np.testing.assert_allclose(got[:, 5], d.astype(np.float64).mean(axis=1), atol=5e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# bin power
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('kind', ['mean', 'rms', 'max', 'peak', 'min', 'median', 0.25])
+@pytest.mark.parametrize('nbin', [1, 7, 100, 1536, 50000, 150000])
+def test_bin_power_vs_oracle(cuda_device, kind, nbin):
+    x = synth(3, (3, 300001))
+    ref = orc.iq_to_bin_power(x, 1.0, float(nbin), kind=kind, axis=1, truncate=True)
+    got = iqw.iq_to_bin_power(dev_of(x, cuda_device), 1.0, float(nbin), kind=kind, axis=1, truncate=True)
+    assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
+    rtol = 2e-6 if kind in ('mean', 'rms') else 1e-6
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=rtol)
+
+
+def test_bin_power_golden_and_layouts(cuda_device):
+    p, a = load_golden('binpower_1536')
+    xd = dev_of(a['x'], cuda_device)
+    for kind in ('mean', 'max', 'min', 'median', 'rms', 'peak'):
+        got = iqw.iq_to_bin_power(xd, kind=kind, **p).cpu().numpy()
+        np.testing.assert_allclose(got, a[kind], rtol=2e-6)
+    np.testing.assert_allclose(iqw.iq_to_bin_power(xd, kind=0.25, **p).cpu().numpy(), a['q25'], rtol=1e-6)
+    # 1-D and time-axis-first layouts
+    q = dict(p, axis=0)
+    got = iqw.iq_to_bin_power(xd[1], kind='mean', **q).cpu().numpy()
+    np.testing.assert_allclose(got, a['mean'][1], rtol=2e-6)
+    got = iqw.iq_to_bin_power(xd.T.contiguous(), kind='max', **q).cpu().numpy()
+    np.testing.assert_allclose(got, a['max'].T, rtol=1e-6)
+    # unaligned start (odd element offset -> scalar peel path)
+    got = iqw.iq_to_bin_power(xd[0, 1:], 1.0, 1537.0, kind='mean', truncate=True).cpu().numpy()
+    ref = orc.iq_to_bin_power(a['x'][0, 1:], 1.0, 1537.0, kind='mean', truncate=True)
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
