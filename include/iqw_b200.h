@@ -127,6 +127,15 @@ int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_channel_str
 int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_channel_stride,
                                 int64_t bin_len, int64_t n_bins, float* d_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement aid (no reference counterpart): when enabled, every kernel launch of the library is
+ * bracketed by CUDA events on the launching stream.  iqw_profile_report writes one text line per
+ * kernel name, "<name> <launches> <total_ms>\n"; call it after synchronising the stream(s).
+ */
+int iqw_profile_enable(int on);
+int iqw_profile_reset(void);
+int iqw_profile_report(char* buf, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

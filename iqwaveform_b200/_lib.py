@@ -52,6 +52,9 @@ SIGNATURES = {
     'iqw_bin_power_workspace_bytes': (_sz, [_i64, _i64, _i64]),
     'iqw_bin_power_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     'iqw_envtopow_transposed_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    'iqw_profile_enable': (ctypes.c_int, [ctypes.c_int]),
+    'iqw_profile_reset': (ctypes.c_int, []),
+    'iqw_profile_report': (ctypes.c_int, [ctypes.c_char_p, _sz]),
 }
 
 
@@ -92,3 +95,19 @@ def check(status: int) -> None:
     if status == IQW_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise IQWError(f'iqw status {status}: {msg}')
+
+
+def profile(on: bool) -> None:
+    lib.iqw_profile_reset()
+    lib.iqw_profile_enable(int(on))
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total_ms)}; synchronise the device first"""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib.iqw_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out

@@ -1,5 +1,10 @@
 // iqw_abi.cu -- version / error plumbing of the C-ABI (include/iqw_b200.h).
 #include <mutex>
+#include <vector>
+#include <string>
+#include <map>
+#include <atomic>
+#include <cstring>
 #include "iqw_common.cuh"
 
 namespace iqw {
@@ -23,7 +28,50 @@ int device_sm_count(int* sms) {
     return IQW_OK;
 }
 
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mutex;
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+
+bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void profile_push(const char* name, cudaEvent_t a, cudaEvent_t b) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof.push_back({name, a, b});
+}
+
 }  // namespace iqw
 
 extern "C" int iqw_abi_version(void) { return IQW_ABI_VERSION; }
 extern "C" const char* iqw_last_error(void) { return iqw::last_error_buffer(); }
+
+extern "C" int iqw_profile_enable(int on) { iqw::g_prof_on.store(on != 0); return IQW_OK; }
+
+extern "C" int iqw_profile_reset(void) {
+    std::lock_guard<std::mutex> lock(iqw::g_prof_mutex);
+    for (auto& r : iqw::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    iqw::g_prof.clear();
+    return IQW_OK;
+}
+
+// one line per kernel name: "<name> <launches> <total_ms>\n"; call after synchronising the stream
+extern "C" int iqw_profile_report(char* buf, size_t cap) {
+    std::lock_guard<std::mutex> lock(iqw::g_prof_mutex);
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto& r : iqw::g_prof) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, r.a, r.b);
+        if (e != cudaSuccess) return iqw::fail(IQW_ERR_CUDA, "profile: %s", cudaGetErrorString(e));
+        auto& x = agg[r.name];
+        x.first += 1;
+        x.second += ms;
+    }
+    std::string out;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof line, "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (out.size() + 1 > cap) return iqw::fail(IQW_ERR_INVALID, "profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return IQW_OK;
+}

@@ -209,7 +209,7 @@ extern "C" int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_
         long long blocks = (bins + kBpThreads / 32 - 1) / (kBpThreads / 32);
         const long long cap = (long long)sms * 16;
         if (blocks > cap) blocks = cap;
-        bin_power_warp_kernel<<<(unsigned)blocks, kBpThreads, 0, s>>>(a);
+        { IQW_PROFILE("bin_power_warp", s); bin_power_warp_kernel<<<(unsigned)blocks, kBpThreads, 0, s>>>(a); }
         IQW_CUDA_OK(cudaGetLastError());
         return IQW_OK;
     }
@@ -239,7 +239,7 @@ extern "C" int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_
     long long blocks = a.n_items;
     const long long cap = (long long)sms * 32;
     if (blocks > cap) blocks = cap;
-    bin_power_cta_kernel<<<(unsigned)blocks, kBpThreads, 0, s>>>(a);
+    { IQW_PROFILE("bin_power_cta", s); bin_power_cta_kernel<<<(unsigned)blocks, kBpThreads, 0, s>>>(a); }
     IQW_CUDA_OK(cudaGetLastError());
     return IQW_OK;
 }

@@ -28,6 +28,21 @@ inline int fail(int code, const char* fmt, ...) {
 
 int device_sm_count(int* sms);
 
+// Optional per-kernel timing (off by default; bench.py turns it on): every launch site is wrapped
+// in a scope that records a CUDA event before and after the launch ON THE LAUNCHING STREAM.
+bool profile_enabled();
+void profile_push(const char* name, cudaEvent_t a, cudaEvent_t b);
+struct ProfScope {
+    const char* name; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(const char* n, cudaStream_t st) : name(n), s(st) {
+        if (profile_enabled()) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() { if (a) { cudaEventRecord(b, s); profile_push(name, a, b); } }
+};
+#define IQW_CAT2(a, b) a##b
+#define IQW_CAT(a, b) IQW_CAT2(a, b)
+#define IQW_PROFILE(name, stream) ::iqw::ProfScope IQW_CAT(_prof_, __LINE__)(name, stream)
+
 // order-preserving map float32 -> uint32 (total order: -nan < -inf < ... < -0 < +0 < ... < +inf < nan)
 __host__ __device__ __forceinline__ uint32_t float_to_key(float f) {
 #if defined(__CUDA_ARCH__)

@@ -603,10 +603,12 @@ static void launch_refine_collect(dim3 grid, size_t rf_smem, cudaStream_t s, con
                                   Work w, unsigned cblocks, unsigned cthreads) {
     cudaFuncSetAttribute(refine_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_smem);
     for (int level = 0; level < kRefineLevels; ++level) {
-        refine_kernel<M><<<grid, kBX, rf_smem, s>>>(p, rows, cols, rps, w);
-        scan_refine_kernel<<<cblocks, cthreads, 0, s>>>(cols, rp, w);
+        static const char* const names[kRefineLevels] = {"stats_refine_1", "stats_refine_2", "stats_refine_3",
+                                                        "stats_refine_4", "stats_refine_5", "stats_refine_6"};
+        { IQW_PROFILE(names[level], s); refine_kernel<M><<<grid, kBX, rf_smem, s>>>(p, rows, cols, rps, w); }
+        { IQW_PROFILE("stats_scan", s); scan_refine_kernel<<<cblocks, cthreads, 0, s>>>(cols, rp, w); }
     }
-    collect_kernel<M><<<grid, kBX, 0, s>>>(p, rows, cols, rps, w);
+    { IQW_PROFILE("stats_collect", s); collect_kernel<M><<<grid, kBX, 0, s>>>(p, rows, cols, rps, w); }
 }
 
 }  // namespace iqw
@@ -678,18 +680,21 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
         float* out = d_out + c * (int64_t)n_stats * n_cols;
 
         IQW_CUDA_OK(cudaMemsetAsync(d_workspace, 0, w.zero_bytes, s));
-        init_ff_kernel<<<cblocks, cthreads, 0, s>>>(w.range_lo, w.kmin, n_cols);
+        { IQW_PROFILE("stats_init", s); init_ff_kernel<<<cblocks, cthreads, 0, s>>>(w.range_lo, w.kmin, n_cols); }
 
-        range_kernel<<<dim3((unsigned)col_tiles, (unsigned)rsplits), kBX, 0, s>>>(p, n_rows, n_cols, row_step, w);
+        { IQW_PROFILE("stats_range", s); range_kernel<<<dim3((unsigned)col_tiles, (unsigned)rsplits), kBX, 0, s>>>(p, n_rows, n_cols, row_step, w); }
+        {
+        IQW_PROFILE("stats_l0", s);
         if (want_sum && to_dB)
             l0_kernel<true, true><<<grid, kBX, l0_smem, s>>>(p, n_rows, n_cols, rows_per_split, eps, w);
         else if (want_sum)
             l0_kernel<true, false><<<grid, kBX, l0_smem, s>>>(p, n_rows, n_cols, rows_per_split, eps, w);
         else
             l0_kernel<false, false><<<grid, kBX, l0_smem, s>>>(p, n_rows, n_cols, rows_per_split, eps, w);
+        }
 
         if (rp.n_ranks > 0) {
-            scan0_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, rp, w);
+            { IQW_PROFILE("stats_scan", s); scan0_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, rp, w); }
             if (m_pad == 2)
                 launch_refine_collect<2>(grid, rf_smem, s, p, n_rows, n_cols, rows_per_split, rp, w, cblocks, cthreads);
             else if (m_pad == 4)
@@ -697,7 +702,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
             else
                 launch_refine_collect<8>(grid, rf_smem, s, p, n_rows, n_cols, rows_per_split, rp, w, cblocks, cthreads);
         }
-        resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_rows, n_cols, rp, st, to_dB, eps, w, out);
+        { IQW_PROFILE("stats_resolve", s); resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_rows, n_cols, rp, st, to_dB, eps, w, out); }
         IQW_CUDA_OK(cudaGetLastError());
     }
     return IQW_OK;

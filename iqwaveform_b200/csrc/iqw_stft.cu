@@ -204,7 +204,7 @@ static int launch_stft(StftArgs a, cudaStream_t stream) {
     a.n_groups = a.groups_per_ch * a.n_channels;
     long long grid = (long long)sms * per_sm;
     if (grid > a.n_groups) grid = a.n_groups;
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(a);
+    { IQW_PROFILE("stft_kernel", stream); kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(a); }
     IQW_CUDA_OK(cudaGetLastError());
     return IQW_OK;
 }
