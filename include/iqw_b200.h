@@ -127,6 +127,12 @@ int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_channel_str
 int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_channel_stride,
                                 int64_t bin_len, int64_t n_bins, float* d_out, void* stream);
 
+/* Test aid: width of the brackets the row sample puts around each target rank on the long-column
+ * path of iqw_time_stats_f32 (default 6 sigma + 2 ranks).  Results are exact for ANY setting -- a
+ * bracket that misses its rank is refined like any other interval -- which is what the tests use
+ * this for (margin 0 makes about half of the brackets miss). */
+int iqw_debug_set_sample_margin(double sigmas, int extra_ranks);
+
 /* ---------------------------------------------------------------------------------------------
  * Measurement aid (no reference counterpart): when enabled, every kernel launch of the library is
  * bracketed by CUDA events on the launching stream.  iqw_profile_report writes one text line per

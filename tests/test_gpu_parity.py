@@ -260,6 +260,32 @@ def test_time_statistics_bitwise(cuda_device, T, nb):
     np.testing.assert_allclose(got[:, 8], truth, rtol=1e-6, atol=1e-7 * np.abs(a).max())
 
 
+@pytest.mark.parametrize('sigmas,extra', [(0.0, 0), (0.5, 0), (6.0, 2)])
+def test_sampled_path_is_exact_even_when_brackets_miss(cuda_device, sigmas, extra):
+    """long columns take the row-sample -> bracket path; with a zero margin about half of the
+    brackets miss their rank and the result must still be bitwise equal to numpy"""
+    from iqwaveform_b200 import _lib
+    rng = np.random.default_rng(11)
+    T, nb = 120000, 200
+    a = rng.standard_normal((1, T, nb)).astype(np.float32)
+    a[0, :, 0] = np.sort(a[0, :, 0])                       # trend: early rows small, late rows large
+    a[0, :, 1] = np.where(np.arange(T) % 7 == 3, 100.0, a[0, :, 1])      # periodic bursts
+    a[0, :, 2] = np.round(a[0, :, 2] * 2) / 2              # few distinct values, heavy ties
+    a[0, :, 3] = 0.25                                      # constant
+    a[0, T // 2:, 4] += 50.0                               # level shift half way (bimodal)
+    a[0, :, 5] = np.exp(8 * a[0, :, 5])                    # 70 dB of dynamic range
+    qs = [0.001, 0.1, 0.5, 0.999]
+    try:
+        _lib.lib.iqw_debug_set_sample_margin(sigmas, extra)
+        got = iqw.time_statistics(dev_of(a, cuda_device), qs + ['min', 'max'], dB=False).cpu().numpy()
+    finally:
+        _lib.lib.iqw_debug_set_sample_margin(6.0, 2)
+    want = np.quantile(a, np.array(qs, dtype=np.float32), axis=1)
+    for i in range(len(qs)):
+        assert np.array_equal(got[:, i], want[i]), (qs[i], np.argwhere(got[:, i] != want[i])[:5])
+    assert np.array_equal(got[:, 4], a.min(axis=1)) and np.array_equal(got[:, 5], a.max(axis=1))
+
+
 def test_time_statistics_dB_is_monotone_image(cuda_device):
     rng = np.random.default_rng(2)
     p = rng.exponential(1e-4, (1, 20000, 96)).astype(np.float32)
