@@ -133,6 +133,14 @@ int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_c
  * this for (margin 0 makes about half of the brackets miss). */
 int iqw_debug_set_sample_margin(double sigmas, int extra_ranks);
 
+/* Test aid: counters of the LAST channel iqw_time_stats_f32 processed with this workspace
+ * (synchronises the device): out[0] intervals still to refine, [1] intervals collected from the
+ * matrix, [2] ranks whose bracket missed, [3] brackets of columns whose candidate lists
+ * overflowed, [4]/[5] brackets handed from the candidate lists back to the matrix passes (heavy
+ * ties), [6] inconsistent candidate lists (a bug if ever non-zero), [7] brackets settled from the
+ * candidate lists alone (the fast path). */
+int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out8);
+
 /* ---------------------------------------------------------------------------------------------
  * Measurement aid (no reference counterpart): when enabled, every kernel launch of the library is
  * bracketed by CUDA events on the launching stream.  iqw_profile_report writes one text line per

@@ -25,15 +25,22 @@
 //   resolve : bitonic sort of the candidates in shared memory -> key of every target rank
 //   finalize: dB, numpy lerp, mean/max/min, store
 //
-// LONG COLUMNS (rows >= 32768): two full reads instead of four.
-//   1. the exact pipeline above runs on a pseudo-random 1-in-k ROW SAMPLE (~16k rows) and returns
-//      sample order statistics that bracket every target rank with a 6-sigma margin
-//   2. `bracket` pass over ALL rows: per column, exact count of keys below / between / above the
-//      brackets and a 32-bucket histogram inside each bracket (+ exact min, max, sum)
-//   3. scan: the counts say exactly which sub-bucket (or, if a bracket missed, which gap) holds
-//      each rank -> intervals of a few hundred keys; a missed bracket simply becomes a wide
-//      interval that the R levels refine, so the result is exact whatever the sample looked like
-//   4. collect + resolve + finalize as above
+// LONG COLUMNS (rows >= 32768): ONE full read of the matrix instead of four.
+//   A. sample_brackets : a stratified, jittered ROW SAMPLE (<= 8192 rows) of two columns per CTA is
+//      staged in shared memory; a two-level histogram (2048 bins, then 256 sub-bins around each
+//      wanted sample rank) gives, per group of target ranks, a key BRACKET [lo, hi] that holds the
+//      group's ranks unless the sample was > 6 sigma off
+//   B. bracket_pass    : the single pass over ALL rows.  A thread owns a column and keeps the
+//      brackets in registers; per bracket it counts the keys below it and appends the keys inside
+//      it to a private candidate list (~15 % of the elements in total), + exact min / max / sum
+//   C. scan_brackets   : per column, the exact counts say which bracket (or, after a miss or a list
+//      overflow, which gap) holds each rank -> SELECT intervals (candidates are in the lists) or,
+//      rarely, generic intervals that the exact pipeline above refines from the matrix
+//   D. select          : one CTA per column histograms its candidate lists (2048 bins per bracket),
+//      collects the few keys in the target bins and ranks them -> key of every target rank
+//   E. refine / collect / resolve of the exact pipeline run only for what is still open (they exit
+//      at once otherwise), then finalize.
+// The result is exact for ANY sample: brackets only decide which keys are set aside.
 //
 // Keys are the order-preserving uint32 image of the float (iqw_common.cuh float_to_key), so the
 // selection is exact for any input, ties and signed zeros included.  NaNs sort above +inf.
@@ -51,10 +58,18 @@ constexpr int kRefineLevels = 7;   // 32 key bits / 5 bits per level
 constexpr int kBX = 128;           // columns (= threads) per CTA in the streaming passes
 constexpr int kUnroll = 8;         // rows in flight per thread
 constexpr long long kSampleMinRows = 32768;   // below this the exact pipeline reads all rows
-constexpr long long kSampleRows = 16384;      // target size of the row sample
-constexpr int kMaxGroups = 4;      // rank groups (brackets) per call on the sampled path
+constexpr int kSampleRows = 8192;  // rows of the sample staged in shared memory (per column)
+constexpr int kSampleCols = 2;     // columns per CTA of sample_brackets
+constexpr int kMaxGroups = 8;      // rank groups (brackets) per call on the sampled path
+constexpr int kSelBins = 2048;     // level-1 bins of sample_brackets and select
+constexpr int kSubBins = 256;      // level-2 sub-bins of sample_brackets
+constexpr int kSelBuf = 512;       // keys ranked in shared memory at the end of select
+constexpr int kSelThreads = 512;
+constexpr int kMaxSplits = 512;    // row splits of the bracket pass (select stages their counts)
+constexpr long long kBracketCtas = 148 * 64;   // CTAs the bracket pass aims at (a few waves)
+constexpr long long kMinRowsPerSplit = 256;
 
-enum IvStatus : uint32_t { IV_REFINE = 0, IV_COLLECT = 1, IV_RESOLVED = 2, IV_BRACKET = 3 };
+enum IvStatus : uint32_t { IV_REFINE = 0, IV_COLLECT = 1, IV_RESOLVED = 2, IV_SELECT = 3 };
 
 struct RankPlan {                  // same for every column: depends only on the row count
     int n_ranks;
@@ -68,12 +83,14 @@ struct StatPlan {
     float gamma[kMaxStats];
 };
 
-// which sample order statistics bracket which group of full-matrix ranks
+// which sample order statistics bracket which group of full-matrix ranks, and how many candidate
+// keys each bracket may set aside per (row split, column)
 struct BracketPlan {
     int n_groups;
-    int first[kMaxGroups], nr[kMaxGroups];       // target ranks [first, first+nr) of the full plan
-    int s_lo[kMaxGroups], s_hi[kMaxGroups];      // indices into the SAMPLE RankPlan
-    int open_lo[kMaxGroups], open_hi[kMaxGroups];  // bracket extends to the end of the key space
+    int n_sranks;
+    unsigned int srank[2 * kMaxGroups];          // ascending, distinct sample ranks
+    int s_lo[kMaxGroups], s_hi[kMaxGroups];      // indices into srank, -1 = open end of key space
+    unsigned int cap_sum;                        // keys a (row split, column) candidate list holds
 };
 
 // rows visited by a streaming pass: all of them (step == 1) or one pseudo-random row out of every
@@ -99,32 +116,44 @@ struct Work {
     uint32_t* hist0;      // [cols][256]
     uint32_t* n_iv;       // [cols]
     uint32_t* iv_klo;     // [cols][8]  first key of the interval
-    uint32_t* iv_khi;     // [cols][8]  last key (COLLECT, BRACKET)
-    uint32_t* iv_shift;   // [cols][8]  sub-bucket shift (REFINE, BRACKET)
+    uint32_t* iv_khi;     // [cols][8]  last key
+    uint32_t* iv_shift;   // [cols][8]  sub-bucket shift (REFINE) / bracket slot (SELECT)
     uint32_t* iv_below;   // [cols][8]  number of keys < klo in the column
     uint32_t* iv_status;  // [cols][8]
     uint32_t* iv_first;   // [cols][8]  first target-rank index inside
     uint32_t* iv_nr;      // [cols][8]  number of target ranks inside
-    uint32_t* iv_cnt;     // [cols][8]  number of keys inside (COLLECT: checked against the cursor)
-    uint32_t* r_key;      // [cols][8]  key of each target rank once known
+    uint32_t* iv_cnt;     // [cols][8]  number of keys inside (checked against what is collected)
+    uint32_t* r_key;      // [cols][8]  key of each target rank once known (0xFFFFFFFF = NaN until then)
     uint32_t* hist1;      // [cols][8][32]
-    uint32_t* gap;        // [cols][9]   bracket pass: keys below / between / above the brackets
     uint32_t* cursor;     // [cols][8]
     uint32_t* cand;       // [cols][8][kCap]
-    uint32_t* pending;    // [1] number of intervals in IV_REFINE
+    uint32_t* pending;    // [0] intervals in IV_REFINE, [1] intervals in IV_COLLECT; diagnostics:
+                          // [2] ranks found in a gap (bracket missed), [3] brackets of overflowed
+                          // columns, [4] SELECT intervals handed on as COLLECT, [5] as REFINE,
+                          // [6] inconsistent candidate lists, [7] SELECT intervals
+    // long-column path
+    uint32_t* bk_lo;      // [cols][kMaxGroups] bracket bounds (empty slot: lo > hi)
+    uint32_t* bk_hi;
+    uint32_t* t_below;    // [cols][kMaxGroups] keys below each bracket, all rows
+    uint32_t* t_cnt;      // [cols][kMaxGroups] keys inside each bracket, all rows
+    uint32_t* t_ovf;      // [cols] != 0: some candidate list of the column overflowed
+    uint32_t* s_cnt;      // [splits][cols] keys in each candidate list
+    uint32_t* lists;      // [splits][cols][cap_sum] candidate keys (of all brackets, unordered)
     size_t zero_bytes;    // leading bytes that must be zero before a pipeline starts
+    size_t ff_bytes;      // bytes after them that must be 0xFF
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t carve_work(void* base, int64_t cols, Work* w) {
+// long-column layout: splits == 0 carves the exact pipeline only
+static size_t carve_work(void* base, int64_t cols, int64_t splits, int64_t cap_sum, Work* w) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         void* p = base ? static_cast<char*>(base) + off : nullptr;
         off = align_up(off + bytes, 256);
         return p;
     };
-    const size_t c = (size_t)cols, m = kMaxRanks;
+    const size_t c = (size_t)cols, m = kMaxRanks, g = kMaxGroups;
     Work t{};
     // --- zero-initialised region first ---
     t.range_hi = (uint32_t*)take(4 * c);
@@ -132,14 +161,20 @@ static size_t carve_work(void* base, int64_t cols, Work* w) {
     t.dsum = (double*)take(8 * c);
     t.hist0 = (uint32_t*)take(4 * c * kNB0);
     t.hist1 = (uint32_t*)take(4 * c * m * kNSub);
-    t.gap = (uint32_t*)take(4 * c * (m + 1));
     t.cursor = (uint32_t*)take(4 * c * m);
     t.n_iv = (uint32_t*)take(4 * c);
     t.pending = (uint32_t*)take(256);
+    if (splits > 0) {
+        t.t_below = (uint32_t*)take(4 * c * g);
+        t.t_cnt = (uint32_t*)take(4 * c * g);
+        t.t_ovf = (uint32_t*)take(4 * c);
+    }
     t.zero_bytes = off;
     // --- 0xFF-initialised ---
     t.range_lo = (uint32_t*)take(4 * c);
     t.kmin = (uint32_t*)take(4 * c);
+    t.r_key = (uint32_t*)take(4 * c * m);
+    t.ff_bytes = off - t.zero_bytes;
     // --- written before read ---
     t.iv_klo = (uint32_t*)take(4 * c * m);
     t.iv_khi = (uint32_t*)take(4 * c * m);
@@ -149,8 +184,13 @@ static size_t carve_work(void* base, int64_t cols, Work* w) {
     t.iv_first = (uint32_t*)take(4 * c * m);
     t.iv_nr = (uint32_t*)take(4 * c * m);
     t.iv_cnt = (uint32_t*)take(4 * c * m);
-    t.r_key = (uint32_t*)take(4 * c * m);
     t.cand = (uint32_t*)take(4 * c * m * kCap);
+    if (splits > 0) {
+        t.bk_lo = (uint32_t*)take(4 * c * g);
+        t.bk_hi = (uint32_t*)take(4 * c * g);
+        t.s_cnt = (uint32_t*)take(4 * (size_t)splits * c);
+        t.lists = (uint32_t*)take(4 * (size_t)splits * c * (size_t)cap_sum);
+    }
     if (w) *w = t;
     return off;
 }
@@ -313,6 +353,7 @@ __device__ void iv_append(IvList& L, const Work& w, long long col, uint32_t klo,
         for (uint32_t q = 0; q < nr; ++q) w.r_key[col * kMaxRanks + first + q] = single ? key_exact : klo;
     } else if (cnt <= (uint32_t)kCap) {
         L.status[i] = IV_COLLECT;
+        atomicAdd(w.pending + 1, 1u);
     } else {
         L.status[i] = IV_REFINE;
         const uint32_t l = ceil_log2_u64(span);
@@ -433,35 +474,54 @@ __global__ void scan_refine_kernel(long long cols, RankPlan rp, Work w) {
     iv_store(L, w, col);
 }
 
-// after the bracket pass: regions in key order are gap0, bracket0, gap1, bracket1, ..., gapM with
-// exact counts; locate every target rank in its region
-__global__ void scan_bracket_kernel(long long cols, RankPlan rp, Work w) {
+// after the bracket pass (long-column path): regions in key order are gap, bracket 0, gap,
+// bracket 1, ..., gap with exact counts; locate every target rank in its region.  A rank inside a
+// bracket whose lists did not overflow becomes a SELECT interval (its keys are in the candidate
+// lists); anything else becomes a generic interval that the exact pipeline refines.
+__global__ void scan_brackets_kernel(long long cols, long long rows, RankPlan rp, int n_groups,
+                                     Work w) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= cols) return;
-    IvList O, L;
-    iv_load(O, w, col);
+    IvList L;
     L.n = 0;
     uint32_t cum = 0, i = 0;
-    uint32_t* gap = w.gap + col * (kMaxRanks + 1);
-    for (uint32_t g = 0; g <= O.n; ++g) {
-        const uint32_t c = gap[g];
-        gap[g] = 0;
-        const uint32_t next = cum + c;
-        if (i < (uint32_t)rp.n_ranks && rp.rank[i] < next) {      // the bracket missed: rank is in a gap
+    const uint32_t nrk = (uint32_t)rp.n_ranks;
+    unsigned long long gap_start = 0ull;
+    const uint32_t ovf = w.t_ovf[col];
+    for (int g = 0; g < n_groups && i < nrk; ++g) {
+        const uint32_t lo = w.bk_lo[col * kMaxGroups + g], hi = w.bk_hi[col * kMaxGroups + g];
+        if (lo > hi) continue;                                     // slot merged into an earlier one
+        const uint32_t below = w.t_below[col * kMaxGroups + g], cnt = w.t_cnt[col * kMaxGroups + g];
+        if (rp.rank[i] < below) {                                  // a bracket missed: rank is in the gap
             const uint32_t first = i;
-            while (i < (uint32_t)rp.n_ranks && rp.rank[i] < next) ++i;
-            const unsigned long long start = g == 0 ? 0ull : (unsigned long long)O.khi[g - 1] + 1ull;
-            const unsigned long long end = g == O.n ? 0x100000000ull : (unsigned long long)O.klo[g];
-            iv_append(L, w, col, (uint32_t)start, end - start, cum, c, first, i - first, false, 0u);
+            while (i < nrk && rp.rank[i] < below) ++i;
+            atomicAdd(w.pending + 2, i - first);
+            iv_append(L, w, col, (uint32_t)gap_start, (unsigned long long)lo - gap_start, cum,
+                      below - cum, first, i - first, false, 0u);
         }
-        cum = next;
-        if (g == O.n) break;
-        // ranks inside bracket g; its [first, nr) covers the ranks the plan aimed at it, but after
-        // a miss any rank may land here, so walk with the global rank cursor
-        IvList T = O;
-        T.first[g] = i;
-        T.nr[g] = (uint32_t)rp.n_ranks - i;
-        split_by_subbuckets(L, T, g, w.hist1 + (col * kMaxRanks + g) * kNSub, rp, i, cum, w, col);
+        cum = below;
+        if (i < nrk && rp.rank[i] < cum + cnt) {
+            const uint32_t first = i;
+            while (i < nrk && rp.rank[i] < cum + cnt) ++i;
+            if (ovf || lo == hi) {
+                if (lo != hi) atomicAdd(w.pending + 3, 1u);
+                iv_append(L, w, col, lo, (unsigned long long)hi - lo + 1ull, cum, cnt, first,
+                          i - first, lo == hi, lo);
+            } else {
+                const uint32_t v = L.n++;
+                L.klo[v] = lo; L.khi[v] = hi; L.below[v] = cum; L.cnt[v] = cnt;
+                L.first[v] = first; L.nr[v] = i - first;
+                L.shift[v] = (uint32_t)g; L.status[v] = IV_SELECT;
+                atomicAdd(w.pending + 7, 1u);
+            }
+        }
+        cum += cnt;
+        gap_start = (unsigned long long)hi + 1ull;
+    }
+    if (i < nrk) {                                                 // ranks above the last bracket
+        atomicAdd(w.pending + 2, nrk - i);
+        iv_append(L, w, col, (uint32_t)gap_start, 0x100000000ull - gap_start, cum,
+                  (uint32_t)rows - cum, i, nrk - i, false, 0u);
     }
     iv_store(L, w, col);
 }
@@ -546,49 +606,60 @@ refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long 
     }
 }
 
-// bracket pass over all rows: histogram inside each bracket, counts of the gaps, named statistics
+// bracket pass (long-column path): the ONE read of all rows.  A thread owns a column; its M
+// brackets and 2M counters live in registers.  Per bracket it counts the keys >= lo and the keys
+// > hi (which give the keys below and inside the bracket), and every key inside ANY bracket is
+// appended to the thread's private candidate list of this row split (brackets are disjoint, so
+// the key itself says which bracket it belongs to): no atomics, no shared memory.  A full list
+// keeps counting; the overflow is flagged and the column is refined from the matrix instead.
 template <int M, bool WANT_SUM, bool TO_DB>
 __global__ void __launch_bounds__(kBX)
-bracket_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
-               float eps, Work w) {
-    extern __shared__ uint16_t hist[];   // [M*32 + M + 1][kBX]
+bracket_pass_kernel(const float* __restrict__ p, long long cols, long long rows,
+                    long long rows_per_split, float eps, BracketPlan bp, Work w) {
     const long long col = (long long)blockIdx.x * kBX + threadIdx.x;
-    const int t = threadIdx.x;
-    int active = 0;
-    IvRegs<M> iv;
-    iv.load(w, col, col < cols, IV_BRACKET, active);
-    for (int i = t; i < (M * kNSub + M + 1) * kBX; i += kBX) hist[i] = 0;
-    __syncthreads();
     if (col >= cols) return;
-
+    uint32_t lo[M], hi[M], n_ge[M], n_gt[M];
+#pragma unroll
+    for (int g = 0; g < M; ++g) {
+        lo[g] = w.bk_lo[col * kMaxGroups + g];
+        hi[g] = w.bk_hi[col * kMaxGroups + g];
+        n_ge[g] = 0; n_gt[g] = 0;
+    }
+    const uint32_t cap = bp.cap_sum;
+    uint32_t* __restrict__ list = w.lists + ((long long)blockIdx.y * cols + col) * (long long)cap;
+    uint32_t n_list = 0;
     const long long i0 = (long long)blockIdx.y * rows_per_split;
-    const long long i1 = min(rm.n, i0 + rows_per_split);
+    const long long i1 = min(rows, i0 + rows_per_split);
     Named<WANT_SUM, TO_DB> named;
     auto visit = [&](float f) {
         const uint32_t k = float_to_key(f);
         named.add(f, k, eps);
-        uint32_t kl, kh, sh;
-        const int v = iv.find(k, kl, kh, sh);
-        // inside bracket v -> its sub-bucket; otherwise the gap that follows bracket v (gap v+1)
-        const int slot = (v >= 0 && k <= kh) ? v * kNSub + (int)((k - kl) >> sh) : M * kNSub + v + 1;
-        hist[slot * kBX + t] += 1;
-    };
-    IQW_STREAM(false, p, cols, col, rm, i0, i1, visit);
-
-    uint32_t* g = w.hist1 + col * (kMaxRanks * kNSub);
+        bool inside = false;
 #pragma unroll
-    for (int v = 0; v < M; ++v) {
-        if ((uint32_t)v >= iv.n) break;
-        for (int b = 0; b < kNSub; ++b) {
-            const uint32_t c = hist[(v * kNSub + b) * kBX + t];
-            if (c) atomicAdd(g + v * kNSub + b, c);
+        for (int g = 0; g < M; ++g) {
+            const bool ge = k >= lo[g], gt = k > hi[g];
+            n_ge[g] += ge ? 1u : 0u;
+            n_gt[g] += gt ? 1u : 0u;
+            inside |= ge && !gt;
+        }
+        if (inside) {
+            if (n_list < cap) list[n_list] = k;
+            ++n_list;
+        }
+    };
+    RowMap all{rows, 1, 0u};
+    stream_column<false>(p, cols, col, all, i0, i1, visit);
+
+    const uint32_t n = (uint32_t)(i1 > i0 ? i1 - i0 : 0);
+#pragma unroll
+    for (int g = 0; g < M; ++g) {
+        if (g < bp.n_groups && lo[g] <= hi[g]) {
+            if (n - n_ge[g]) atomicAdd(w.t_below + col * kMaxGroups + g, n - n_ge[g]);
+            if (n_ge[g] - n_gt[g]) atomicAdd(w.t_cnt + col * kMaxGroups + g, n_ge[g] - n_gt[g]);
         }
     }
-    uint32_t* gg = w.gap + col * (kMaxRanks + 1);
-    for (uint32_t v = 0; v <= iv.n; ++v) {
-        const uint32_t c = hist[(M * kNSub + v) * kBX + t];
-        if (c) atomicAdd(gg + v, c);
-    }
+    w.s_cnt[(long long)blockIdx.y * cols + col] = min(n_list, cap);
+    if (n_list > cap) atomicOr(w.t_ovf + col, 1u);
     named.flush(w, col);
 }
 
@@ -596,6 +667,7 @@ template <int M>
 __global__ void __launch_bounds__(kBX)
 collect_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
                Work w) {
+    if (w.pending[1] == 0) return;
     const long long col = (long long)blockIdx.x * kBX + threadIdx.x;
     int active = 0;
     IvRegs<M> iv;
@@ -626,6 +698,7 @@ constexpr int kResolveThreads = 256;
 __global__ void __launch_bounds__(kResolveThreads)
 resolve_kernel(long long cols, RankPlan rp, Work w) {
     __shared__ uint32_t keys[kCap];
+    if (w.pending[1] == 0) return;
     const long long col = blockIdx.x;
     const int t = threadIdx.x;
     const uint32_t n_iv = w.n_iv[col];
@@ -662,32 +735,414 @@ resolve_kernel(long long cols, RankPlan rp, Work w) {
     }
 }
 
-// sample order statistics -> brackets of the full pass (one thread per column)
-__global__ void make_brackets_kernel(long long cols, BracketPlan bp, Work ws, Work wf) {
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= cols) return;
-    IvList L;
-    L.n = 0;
-    for (int g = 0; g < bp.n_groups; ++g) {
-        const uint32_t lo = bp.open_lo[g] ? 0u : ws.r_key[col * kMaxRanks + bp.s_lo[g]];
-        const uint32_t hi = bp.open_hi[g] ? 0xFFFFFFFFu : ws.r_key[col * kMaxRanks + bp.s_hi[g]];
-        if (L.n > 0 && lo <= L.khi[L.n - 1]) {          // overlaps the previous bracket: merge
-            const uint32_t i = L.n - 1;
-            L.khi[i] = max(L.khi[i], hi);
-            L.nr[i] += bp.nr[g];
-        } else {
-            const uint32_t i = L.n++;
-            L.klo[i] = lo; L.khi[i] = max(hi, lo);
-            L.first[i] = bp.first[g]; L.nr[i] = bp.nr[g];
-            L.below[i] = 0; L.cnt[i] = 0; L.status[i] = IV_BRACKET;
+// ---------------------------------------------------------------------------------------------
+// long-column path, step A: row sample -> brackets.  One CTA stages the sampled keys of
+// kSampleCols adjacent columns in shared memory and locates the wanted SAMPLE ranks with a
+// two-level histogram; the bracket bounds are bin edges (a little wider than the sample order
+// statistics, never narrower), which is all the bracket pass needs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSampleThreads = 512;
+constexpr int kSR = 2 * kMaxGroups;   // sample ranks per column
+constexpr size_t kSampleSmem =
+    sizeof(uint32_t) * ((size_t)kSampleCols * kSampleRows + (size_t)kSampleCols * kSR * kSubBins);
+static_assert(kSampleCols * kSR * kSubBins >= kSampleCols * kSelBins, "level-1 bins reuse the level-2 area");
+
+__device__ __forceinline__ uint32_t sel_shift(uint32_t span, uint32_t bins) {
+    uint32_t s = 0;
+    while ((span >> s) >= bins) ++s;
+    return s;
+}
+
+__global__ void __launch_bounds__(kSampleThreads)
+sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, BracketPlan bp, Work w) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* keys = smem_u32;                                   // [kSampleCols][kSampleRows]
+    uint32_t* hist = keys + kSampleCols * kSampleRows;           // level 1: [kSampleCols][kSelBins]
+                                                                 // level 2: [kSampleCols][kSR][kSubBins]
+    __shared__ uint32_t s_min[kSampleCols], s_max[kSampleCols];
+    __shared__ uint32_t s_bin[kSampleCols][kSR], s_below[kSampleCols][kSR], s_slot[kSampleCols][kSR];
+    __shared__ uint32_t s_elo[kSampleCols][kSR], s_ehi[kSampleCols][kSR];
+
+    const int t = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * kSampleCols;
+    const int S = (int)rm.n;
+    const int nsr = bp.n_sranks;
+    if (t < kSampleCols) { s_min[t] = 0xFFFFFFFFu; s_max[t] = 0u; }
+    for (int i = t; i < kSampleCols * kSelBins; i += kSampleThreads) hist[i] = 0;
+    __syncthreads();
+
+    // ---- stage the sample, min / max per column ----
+    uint32_t mn[kSampleCols], mx[kSampleCols];
+#pragma unroll
+    for (int c = 0; c < kSampleCols; ++c) { mn[c] = 0xFFFFFFFFu; mx[c] = 0u; }
+    constexpr int U = 8;                       // rows in flight per thread
+    for (int i0 = 0; i0 < S; i0 += kSampleThreads * U) {
+        float v[U][kSampleCols];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kSampleThreads + t;
+            if (i < S) {
+                const float* src = p + map_row(rm, i) * cols + c0;
+#pragma unroll
+                for (int c = 0; c < kSampleCols; ++c) v[u][c] = (c0 + c < cols) ? __ldg(src + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kSampleThreads + t;
+            if (i < S) {
+#pragma unroll
+                for (int c = 0; c < kSampleCols; ++c) {
+                    const uint32_t k = float_to_key(v[u][c]);
+                    keys[c * kSampleRows + i] = k;
+                    mn[c] = min(mn[c], k);
+                    mx[c] = max(mx[c], k);
+                }
+            }
         }
     }
-    for (uint32_t i = 0; i < L.n; ++i) {
-        const unsigned long long span = (unsigned long long)L.khi[i] - L.klo[i] + 1ull;
-        const uint32_t l = ceil_log2_u64(span);
-        L.shift[i] = l > 5 ? l - 5 : 0;
+#pragma unroll
+    for (int c = 0; c < kSampleCols; ++c) {
+        mn[c] = __reduce_min_sync(0xFFFFFFFFu, mn[c]);
+        mx[c] = __reduce_max_sync(0xFFFFFFFFu, mx[c]);
+        if ((t & 31) == 0) { atomicMin(&s_min[c], mn[c]); atomicMax(&s_max[c], mx[c]); }
     }
-    iv_store(L, wf, col);
+    __syncthreads();
+
+    // ---- level 1: kSelBins bins over [min, max] ----
+    uint32_t kmin[kSampleCols], sh1[kSampleCols];
+#pragma unroll
+    for (int c = 0; c < kSampleCols; ++c) {
+        kmin[c] = s_min[c];
+        sh1[c] = sel_shift(s_max[c] - s_min[c], kSelBins);
+    }
+    for (int i = t; i < S; i += kSampleThreads) {
+#pragma unroll
+        for (int c = 0; c < kSampleCols; ++c)
+            if (c0 + c < cols) atomicAdd(&hist[c * kSelBins + ((keys[c * kSampleRows + i] - kmin[c]) >> sh1[c])], 1u);
+    }
+    __syncthreads();
+    {   // warp c scans column c: lane owns kSelBins/32 consecutive bins
+        const int c = t >> 5, lane = t & 31;
+        if (c < kSampleCols && c0 + c < cols) {
+            constexpr int PER = kSelBins / 32;
+            const uint32_t* h = hist + c * kSelBins + lane * PER;
+            uint32_t sum = 0;
+            for (int b = 0; b < PER; ++b) sum += h[b];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            uint32_t cum = inc - sum;
+            int j = 0;
+            while (j < nsr && bp.srank[j] < cum) ++j;
+            for (int b = 0; b < PER && j < nsr; ++b) {
+                const uint32_t hb = h[b];
+                while (j < nsr && bp.srank[j] < cum + hb) {
+                    s_bin[c][j] = (uint32_t)(lane * PER + b);
+                    s_below[c][j] = cum;
+                    ++j;
+                }
+                cum += hb;
+            }
+        }
+    }
+    __syncthreads();
+    if (t < kSampleCols) {      // sample ranks that share a level-1 bin share a level-2 histogram
+        for (int j = 0; j < nsr; ++j)
+            s_slot[t][j] = (j > 0 && s_bin[t][j] == s_bin[t][j - 1]) ? s_slot[t][j - 1] : (uint32_t)j;
+    }
+    for (int i = t; i < kSampleCols * kSR * kSubBins; i += kSampleThreads) hist[i] = 0;
+    __syncthreads();
+
+    // ---- level 2: kSubBins sub-bins inside each wanted bin ----
+    for (int i = t; i < S; i += kSampleThreads) {
+#pragma unroll
+        for (int c = 0; c < kSampleCols; ++c) {
+            if (c0 + c >= cols) continue;
+            const uint32_t d = keys[c * kSampleRows + i] - kmin[c];
+            const uint32_t b = d >> sh1[c];
+            const uint32_t sh2 = sh1[c] > 8 ? sh1[c] - 8 : 0;
+            for (int j = 0; j < nsr; ++j) {
+                if (s_bin[c][j] == b && s_slot[c][j] == (uint32_t)j) {
+                    atomicAdd(&hist[(c * kSR + j) * kSubBins + ((d - (b << sh1[c])) >> sh2)], 1u);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // one warp per (column, sample rank): sub-bin holding the rank -> key edges
+    for (int task = t >> 5; task < kSampleCols * nsr; task += kSampleThreads / 32) {
+        const int c = task / nsr, j = task % nsr, lane = t & 31;
+        if (c0 + c >= cols) continue;
+        constexpr int PER = kSubBins / 32;
+        const uint32_t* h = hist + (c * kSR + (int)s_slot[c][j]) * kSubBins + lane * PER;
+        uint32_t sum = 0;
+        for (int b = 0; b < PER; ++b) sum += h[b];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        uint32_t cum = inc - sum;
+        const uint32_t pos = bp.srank[j] - s_below[c][j];
+        if (pos >= cum && pos < cum + sum) {
+            int b = 0;
+            while (pos >= cum + h[b]) { cum += h[b]; ++b; }
+            const uint32_t sh2 = sh1[c] > 8 ? sh1[c] - 8 : 0;
+            const unsigned long long e0 = (unsigned long long)kmin[c] +
+                                          ((unsigned long long)s_bin[c][j] << sh1[c]) +
+                                          ((unsigned long long)(lane * PER + b) << sh2);
+            const unsigned long long e1 = e0 + (1ull << sh2) - 1ull;
+            s_elo[c][j] = (uint32_t)e0;
+            s_ehi[c][j] = e1 > (unsigned long long)s_max[c] ? s_max[c] : (uint32_t)e1;
+        }
+    }
+    __syncthreads();
+
+    // ---- brackets: a group that reaches into its predecessor is merged into it ----
+    if (t < kSampleCols && c0 + t < cols) {
+        const long long col = c0 + t;
+        int last = -1;
+        for (int g = 0; g < kMaxGroups; ++g) {
+            uint32_t lo = 0xFFFFFFFFu, hi = 0u;                    // empty slot
+            if (g < bp.n_groups) {
+                lo = bp.s_lo[g] < 0 ? 0u : s_elo[t][bp.s_lo[g]];
+                hi = bp.s_hi[g] < 0 ? 0xFFFFFFFFu : s_ehi[t][bp.s_hi[g]];
+                if (hi < lo) hi = lo;
+                if (last >= 0 && lo <= w.bk_hi[col * kMaxGroups + last]) {
+                    if (hi > w.bk_hi[col * kMaxGroups + last]) w.bk_hi[col * kMaxGroups + last] = hi;
+                    lo = 0xFFFFFFFFu; hi = 0u;
+                } else {
+                    last = g;
+                }
+            }
+            w.bk_lo[col * kMaxGroups + g] = lo;
+            w.bk_hi[col * kMaxGroups + g] = hi;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// long-column path, step D: one CTA per column ranks the candidate lists of its SELECT intervals.
+// Each sweep reads every list of the column once (a warp per row split, 8 loads in flight per
+// lane).  Sweep 1 histograms the keys (kSelBins bins per bracket); a warp per bracket then finds
+// the bins holding its first and last rank and either
+//   * collects the keys of those bins in a second sweep (a few dozen) and ranks them by counting,
+//   * reads the answer off the histogram when bins are single keys,
+//   * descends into the one bin holding all its ranks (heavy ties) and histograms again, or
+//   * (ranks in different, crowded bins) hands a much narrower generic interval to the exact
+//     pipeline.
+// ---------------------------------------------------------------------------------------------
+enum SelMode : uint32_t { SEL_IDLE = 0, SEL_HIST = 1, SEL_COLLECT = 2 };
+
+template <int M>
+__global__ void __launch_bounds__(kSelThreads, 3)
+select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* hist = smem_u32;                         // [M][kSelBins]
+    uint32_t* buf = hist + M * kSelBins;               // [M][kSelBuf]
+    uint32_t* cnts = buf + M * kSelBuf;                // [splits]
+    __shared__ uint32_t s_a[M], s_b[M], s_sh[M], s_below[M], s_first[M], s_nr[M], s_iv[M];
+    __shared__ uint32_t s_bf[M], s_bl[M], s_cb[M], s_n[M], s_mode[M];
+    __shared__ int s_any;
+
+    const long long col = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int NW = kSelThreads / 32;
+    if (t < M) { s_mode[t] = SEL_IDLE; s_iv[t] = 0xFFFFFFFFu; s_n[t] = 0; s_a[t] = 0xFFFFFFFFu; s_b[t] = 0; s_sh[t] = 0; }
+    if (t == 0) s_any = 0;
+    __syncthreads();
+    if (t == 0) {
+        const uint32_t n_iv = w.n_iv[col];
+        for (uint32_t v = 0; v < n_iv; ++v) {
+            const long long x = col * kMaxRanks + v;
+            if (w.iv_status[x] != IV_SELECT) continue;
+            const uint32_t g = w.iv_shift[x];
+            if (g >= (uint32_t)M) continue;
+            s_iv[g] = v;
+            s_a[g] = w.iv_klo[x]; s_b[g] = w.iv_khi[x];
+            s_sh[g] = sel_shift(s_b[g] - s_a[g], kSelBins);
+            s_below[g] = w.iv_below[x]; s_first[g] = w.iv_first[x]; s_nr[g] = w.iv_nr[x];
+            s_mode[g] = SEL_HIST;
+            s_any = 1;
+        }
+    }
+    __syncthreads();
+    if (!s_any) return;
+    for (int i = t; i < splits; i += kSelThreads) cnts[i] = w.s_cnt[(long long)i * cols + col];
+
+    const uint32_t cap_sum = bp.cap_sum;
+    // bracket of a key among those in `mode` (brackets are disjoint), -1 if none
+    auto bracket_of = [&](uint32_t k, uint32_t mode) {
+        int g = -1;
+#pragma unroll
+        for (int q = 0; q < M; ++q) g = (s_mode[q] == mode && k >= s_a[q] && k <= s_b[q]) ? q : g;
+        return g;
+    };
+    auto sweep = [&](auto&& visit) {
+        const long long stride = cols * (long long)cap_sum;
+        const uint32_t* base = w.lists + (long long)col * cap_sum;
+        for (int sp = warp; sp < splits; sp += NW) {
+            const uint32_t n = cnts[sp];
+            const uint32_t* src = base + (long long)sp * stride;
+            for (uint32_t i0 = 0; i0 < n; i0 += 256) {
+                uint32_t k[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t i = i0 + u * 32 + lane;
+                    k[u] = i < n ? __ldcs(src + i) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + u * 32 + lane < n) visit(k[u]);
+            }
+        }
+    };
+
+    for (int level = 0; level < 4; ++level) {
+        // ---- histogram sweep over the brackets in SEL_HIST ----
+        for (int i = t; i < M * kSelBins; i += kSelThreads) hist[i] = 0;
+        __syncthreads();
+        sweep([&](uint32_t k) {
+            const int g = bracket_of(k, SEL_HIST);
+            if (g >= 0) atomicAdd(&hist[g * kSelBins + ((k - s_a[g]) >> s_sh[g])], 1u);
+        });
+        __syncthreads();
+
+        // ---- a warp per bracket: where are its ranks? ----
+        for (int g = warp; g < M; g += NW) {
+            if (s_mode[g] != SEL_HIST) continue;
+            constexpr int PER = kSelBins / 32;
+            const uint32_t* h = hist + g * kSelBins + lane * PER;
+            uint32_t sum = 0;
+            for (int b = 0; b < PER; ++b) sum += h[b];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const uint32_t pre = inc - sum;
+            const long long x = col * kMaxRanks + s_iv[g];
+            const uint32_t first = s_first[g], nr = s_nr[g], below = s_below[g], sh = s_sh[g];
+            const uint32_t pos_f = rp.rank[first] - below;
+            const uint32_t pos_l = rp.rank[first + nr - 1] - below;
+            const bool sane = pos_l < total && (level > 0 || total == w.iv_cnt[x]);
+            if (sane && sh == 0) {
+                // bins are single keys: every rank reads its key off the histogram
+                for (uint32_t q = 0; q < nr; ++q) {
+                    const uint32_t pos = rp.rank[first + q] - below;
+                    if (pos >= pre && pos < pre + sum) {
+                        uint32_t cum = pre; int b = 0;
+                        while (pos >= cum + h[b]) { cum += h[b]; ++b; }
+                        w.r_key[col * kMaxRanks + first + q] = s_a[g] + (uint32_t)(lane * PER + b);
+                    }
+                }
+            } else if (sane) {
+                if (pos_f >= pre && pos_f < pre + sum) {
+                    uint32_t cum = pre; int b = 0;
+                    while (pos_f >= cum + h[b]) { cum += h[b]; ++b; }
+                    s_bf[g] = (uint32_t)(lane * PER + b); s_cb[g] = cum;
+                }
+                if (pos_l >= pre && pos_l < pre + sum) {
+                    uint32_t cum = pre; int b = 0;
+                    while (pos_l >= cum + h[b]) { cum += h[b]; ++b; }
+                    s_bl[g] = (uint32_t)(lane * PER + b); s_n[g] = cum + h[b];   // keys up to and incl. bin bl
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (!sane) {
+                    s_mode[g] = SEL_IDLE;          // inconsistent lists: ranks stay poisoned (NaN)
+                    atomicAdd(w.pending + 6, 1u);
+                } else if (sh == 0) {
+                    s_mode[g] = SEL_IDLE;
+                    w.iv_status[x] = IV_RESOLVED;
+                } else {
+                    const uint32_t n_mid = s_n[g] - s_cb[g];
+                    const uint32_t klo = s_a[g] + (s_bf[g] << sh);
+                    unsigned long long last = (unsigned long long)s_a[g] + (((unsigned long long)s_bl[g] + 1ull) << sh) - 1ull;
+                    if (last > (unsigned long long)s_b[g]) last = s_b[g];
+                    if (n_mid <= (uint32_t)kSelBuf) {
+                        s_mode[g] = SEL_COLLECT;
+                        s_n[g] = 0;
+                    } else if (s_bf[g] == s_bl[g] && level < 3) {
+                        // all ranks in one crowded bin: histogram that bin next
+                        s_a[g] = klo; s_b[g] = (uint32_t)last;
+                        s_below[g] = below + s_cb[g];
+                        s_sh[g] = sel_shift((uint32_t)last - klo, kSelBins);
+                    } else {
+                        // ranks in different crowded bins: generic interval for the exact pipeline
+                        s_mode[g] = SEL_IDLE;
+                        w.iv_klo[x] = klo; w.iv_khi[x] = (uint32_t)last;
+                        w.iv_below[x] = below + s_cb[g];
+                        w.iv_cnt[x] = n_mid;
+                        if (n_mid <= (uint32_t)kCap) {
+                            w.iv_status[x] = IV_COLLECT; w.iv_shift[x] = 0;
+                            atomicAdd(w.pending + 1, 1u);
+                            atomicAdd(w.pending + 4, 1u);
+                        } else {
+                            const uint32_t l = ceil_log2_u64(last - klo + 1ull);
+                            w.iv_status[x] = IV_REFINE; w.iv_shift[x] = l > 5 ? l - 5 : 0;
+                            atomicAdd(w.pending, 1u);
+                            atomicAdd(w.pending + 5, 1u);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        bool again = false;
+#pragma unroll
+        for (int g = 0; g < M; ++g) again |= s_mode[g] == SEL_HIST;
+        if (!again) break;
+    }
+    bool any_collect = false;
+#pragma unroll
+    for (int g = 0; g < M; ++g) {
+        any_collect |= s_mode[g] == SEL_COLLECT;
+        if (s_mode[g] == SEL_HIST && t == 0) atomicAdd(w.pending + 6, 1u);   // cannot happen (4 levels >= 32 bits)
+    }
+    if (!any_collect) return;
+
+    // ---- second sweep: the keys of the target bins ----
+    sweep([&](uint32_t k) {
+        const int g = bracket_of(k, SEL_COLLECT);
+        if (g < 0) return;
+        const uint32_t b = (k - s_a[g]) >> s_sh[g];
+        if (b >= s_bf[g] && b <= s_bl[g]) {
+            const uint32_t pos = atomicAdd(&s_n[g], 1u);
+            if (pos < (uint32_t)kSelBuf) buf[g * kSelBuf + pos] = k;
+        }
+    });
+    __syncthreads();
+
+    // ---- rank by counting: key e answers position q iff less(e) <= q < less(e) + equal(e) ----
+    for (int g = 0; g < M; ++g) {
+        if (s_mode[g] != SEL_COLLECT) continue;
+        const uint32_t n = min(s_n[g], (uint32_t)kSelBuf);
+        const uint32_t* bk = buf + g * kSelBuf;
+        for (uint32_t e = t; e < n; e += kSelThreads) {
+            const uint32_t ke = bk[e];
+            uint32_t less = 0, eq = 0;
+            for (uint32_t o = 0; o < n; ++o) {
+                const uint32_t ko = bk[o];
+                less += ko < ke ? 1u : 0u;
+                eq += ko == ke ? 1u : 0u;
+            }
+            for (uint32_t q = 0; q < s_nr[g]; ++q) {
+                const uint32_t pos = rp.rank[s_first[g] + q] - s_below[g] - s_cb[g];
+                if (pos >= less && pos < less + eq) w.r_key[col * kMaxRanks + s_first[g] + q] = ke;
+            }
+        }
+        if (t == 0) w.iv_status[col * kMaxRanks + s_iv[g]] = IV_RESOLVED;
+    }
 }
 
 // final rows: dB, numpy lerp, named statistics
@@ -723,11 +1178,6 @@ __global__ void finalize_kernel(long long rows, long long cols, StatPlan st, int
         }
         out[(long long)t * cols + col] = r;
     }
-}
-
-__global__ void init_ff_kernel(uint32_t* a, uint32_t* b, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { a[i] = 0xFFFFFFFFu; b[i] = 0xFFFFFFFFu; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -783,54 +1233,91 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
     return IQW_OK;
 }
 
-// sample plan: group the target ranks, bracket each group by two sample order statistics a
-// 6-sigma (+2) margin away.  Returns false when the sampled path does not apply.
+// long-column plan: row splits of the bracket pass, the row sample, and per group of target
+// ranks the two SAMPLE ranks (margin-sigma away) whose keys bracket it.
 static double g_margin_sigmas = 6.0;   // test aid: iqw_debug_set_sample_margin
 static int g_margin_extra = 2;
 
-static bool build_sample_plan(const RankPlan& rp, int64_t rows, int64_t srows, RankPlan* srp,
-                              BracketPlan* bp) {
+struct LongPlan {
+    long long splits, rows_per_split;
+    RowMap sample;
+    BracketPlan bp;
+};
+
+static void plan_long_shape(int64_t rows, int64_t cols, LongPlan* lp) {
+    const long long col_tiles = (cols + kBX - 1) / kBX;
+    long long splits = kBracketCtas / col_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    long long rps = (rows + splits - 1) / splits;
+    if (rps < kMinRowsPerSplit) rps = kMinRowsPerSplit;
+    lp->rows_per_split = rps;
+    lp->splits = (rows + rps - 1) / rps;
+    long long step = (rows + kSampleRows - 1) / kSampleRows;
+    if (step < 2) step = 2;
+    lp->sample = RowMap{rows / step, step, 0x9E3779B9u};
+}
+
+// widest bracket the default margins produce, in sample ranks (q = 1/2, one statistic's two ranks)
+static long long max_group_width(long long srows) {
+    return 2 * ((long long)std::ceil(6.0 * std::sqrt((double)srows * 0.25)) + 2) + 3;
+}
+
+// candidate-list budget per (row split, column), in keys, for `n_groups` brackets
+static long long cap_budget(const LongPlan& lp, int n_groups) {
+    double f = (double)n_groups * (double)(max_group_width(lp.sample.n) + 2) / (double)lp.sample.n;
+    if (f > 1.0) f = 1.0;
+    return (long long)std::ceil(1.5 * (double)lp.rows_per_split * f) + 32ll * n_groups;
+}
+
+// Returns false when the sampled path does not apply (too many groups).
+static bool build_long_plan(const RankPlan& rp, int64_t rows, int64_t cols, int n_stats, LongPlan* lp) {
+    plan_long_shape(rows, cols, lp);
+    const long long srows = lp->sample.n;
     const double f = (double)srows / (double)rows;
     auto margin = [&](double r) {
         const double q = r / (double)rows;
         return (int64_t)std::ceil(g_margin_sigmas * std::sqrt((double)srows * q * (1.0 - q))) + g_margin_extra;
     };
     int64_t lo[kMaxRanks], hi[kMaxRanks];
-    int first[kMaxRanks], nr[kMaxRanks], ng = 0;
+    int ng = 0;
     for (int i = 0; i < rp.n_ranks; ++i) {
         const int64_t a = (int64_t)std::floor(rp.rank[i] * f) - margin(rp.rank[i]);
         const int64_t b = (int64_t)std::ceil(rp.rank[i] * f) + margin(rp.rank[i]);
         if (ng > 0 && a <= hi[ng - 1]) {               // overlaps the previous group: same bracket
             hi[ng - 1] = b > hi[ng - 1] ? b : hi[ng - 1];
-            nr[ng - 1] += 1;
         } else {
-            lo[ng] = a; hi[ng] = b; first[ng] = i; nr[ng] = 1; ++ng;
+            lo[ng] = a; hi[ng] = b; ++ng;
         }
     }
-    if (ng > kMaxGroups) return false;
-    bp->n_groups = ng;
+    if (ng > kMaxGroups || ng > n_stats) return false;
+    BracketPlan& bp = lp->bp;
+    bp = BracketPlan{};
+    bp.n_groups = ng;
     int64_t sr[2 * kMaxGroups];
     int ns = 0;
     for (int g = 0; g < ng; ++g) {
-        bp->first[g] = first[g]; bp->nr[g] = nr[g];
-        bp->open_lo[g] = lo[g] <= 0;
-        bp->open_hi[g] = hi[g] >= srows - 1;
-        if (!bp->open_lo[g]) sr[ns++] = lo[g];
-        if (!bp->open_hi[g]) sr[ns++] = hi[g];
+        const bool open_lo = lo[g] <= 0, open_hi = hi[g] >= srows - 1;
+        bp.s_lo[g] = open_lo ? -1 : ns;
+        if (!open_lo) sr[ns++] = lo[g];
+        bp.s_hi[g] = open_hi ? -1 : ns;
+        if (!open_hi) sr[ns++] = hi[g];
     }
-    // sample ranks are ascending by construction (groups do not overlap); dedupe defensively
-    int nu = 0;
-    for (int i = 0; i < ns; ++i)
-        if (nu == 0 || sr[i] != sr[nu - 1]) sr[nu++] = sr[i];
-    srp->n_ranks = nu;
-    for (int i = 0; i < nu; ++i) srp->rank[i] = (unsigned)sr[i];
+    // sample ranks are ascending by construction (groups are disjoint); equal neighbours are legal
+    bp.n_sranks = ns;
+    for (int i = 0; i < ns; ++i) bp.srank[i] = (unsigned)sr[i];
+    // candidate capacity per (row split, column): 1.5 x the expected share of the brackets plus
+    // slack, within the budget the workspace was sized for
+    double share = 0.0;
     for (int g = 0; g < ng; ++g) {
-        bp->s_lo[g] = bp->s_hi[g] = 0;
-        for (int k = 0; k < nu; ++k) {
-            if (!bp->open_lo[g] && sr[k] == lo[g]) bp->s_lo[g] = k;
-            if (!bp->open_hi[g] && sr[k] == hi[g]) bp->s_hi[g] = k;
-        }
+        const int64_t a = lo[g] < 0 ? 0 : lo[g], b = hi[g] > srows - 1 ? srows - 1 : hi[g];
+        share += (double)(b - a + 3) / (double)srows;
     }
+    if (share > 1.0) share = 1.0;
+    long long cap = (long long)std::ceil(1.5 * (double)lp->rows_per_split * share) + 32ll * ng;
+    const long long budget = cap_budget(*lp, n_stats < kMaxGroups ? n_stats : kMaxGroups);
+    if (cap > budget) cap = budget;
+    bp.cap_sum = (unsigned)cap;
     return true;
 }
 
@@ -881,21 +1368,34 @@ static void launch_collect(const Grid& g, cudaStream_t s, const float* p, long l
 }
 
 template <int M>
-static void launch_bracket(const Grid& g, cudaStream_t s, const float* p, long long cols, RowMap rm,
-                           bool want_sum, bool to_dB, float eps, const Work& w) {
-    const size_t smem = sizeof(uint16_t) * (M * kNSub + M + 1) * kBX;
-    IQW_PROFILE("stats_bracket", s);
-    if (want_sum && to_dB) {
-        cudaFuncSetAttribute(bracket_kernel<M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bracket_kernel<M, true, true><<<g.grid, kBX, smem, s>>>(p, cols, rm, g.rows_per_split, eps, w);
-    } else if (want_sum) {
-        cudaFuncSetAttribute(bracket_kernel<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bracket_kernel<M, true, false><<<g.grid, kBX, smem, s>>>(p, cols, rm, g.rows_per_split, eps, w);
-    } else {
-        cudaFuncSetAttribute(bracket_kernel<M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        bracket_kernel<M, false, false><<<g.grid, kBX, smem, s>>>(p, cols, rm, g.rows_per_split, eps, w);
-    }
+static void launch_bracket_pass(cudaStream_t s, const float* p, long long cols, long long rows,
+                                const LongPlan& lp, bool want_sum, bool to_dB, float eps, const Work& w) {
+    const dim3 grid((unsigned)((cols + kBX - 1) / kBX), (unsigned)lp.splits);
+    IQW_PROFILE("stats_bracket_pass", s);
+    if (want_sum && to_dB)
+        bracket_pass_kernel<M, true, true><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w);
+    else if (want_sum)
+        bracket_pass_kernel<M, true, false><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w);
+    else
+        bracket_pass_kernel<M, false, false><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w);
 }
+
+template <int M>
+static int launch_select(cudaStream_t s, long long cols, const RankPlan& rp, const LongPlan& lp, const Work& w) {
+    const size_t smem = sizeof(uint32_t) * ((size_t)M * (kSelBins + kSelBuf) + (size_t)lp.splits);
+    IQW_CUDA_OK(cudaFuncSetAttribute(select_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IQW_PROFILE("stats_select", s);
+    select_kernel<M><<<(unsigned)cols, kSelThreads, smem, s>>>(cols, (int)lp.splits, rp, lp.bp, w);
+    return IQW_OK;
+}
+
+#define IQW_DISPATCH_G(m, CALL)                  \
+    do {                                         \
+        if ((m) <= 1) { constexpr int M = 1; CALL; }        \
+        else if ((m) <= 2) { constexpr int M = 2; CALL; }   \
+        else if ((m) <= 4) { constexpr int M = 4; CALL; }   \
+        else { constexpr int M = 8; CALL; }                 \
+    } while (0)
 
 #define IQW_DISPATCH_M(m, CALL)                  \
     do {                                         \
@@ -949,10 +1449,10 @@ static int run_exact(const float* p, long long cols, RowMap rm, const RankPlan& 
     return IQW_OK;
 }
 
-static int reset_work(const Work& w, long long cols, cudaStream_t s) {
-    IQW_CUDA_OK(cudaMemsetAsync(w.range_hi, 0, w.zero_bytes, s));   // range_hi is the first field
-    const unsigned cthreads = 128, cblocks = (unsigned)((cols + cthreads - 1) / cthreads);
-    init_ff_kernel<<<cblocks, cthreads, 0, s>>>(w.range_lo, w.kmin, cols);
+static int reset_work(const Work& w, cudaStream_t s) {
+    // range_hi is the first field of the zero region; the 0xFF region follows it directly
+    IQW_CUDA_OK(cudaMemsetAsync(w.range_hi, 0, w.zero_bytes, s));
+    IQW_CUDA_OK(cudaMemsetAsync(reinterpret_cast<char*>(w.range_hi) + w.zero_bytes, 0xFF, w.ff_bytes, s));
     return IQW_OK;
 }
 
@@ -966,12 +1466,23 @@ extern "C" int iqw_debug_set_sample_margin(double sigmas, int extra) {
     return IQW_OK;
 }
 
+extern "C" int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out8) {
+    if (!d_workspace || !host_out8 || n_cols < 1) return fail(IQW_ERR_INVALID, "bad argument");
+    Work w{};
+    carve_work(const_cast<void*>(d_workspace), n_cols, 0, 0, &w);
+    IQW_CUDA_OK(cudaMemcpy(host_out8, w.pending, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return IQW_OK;
+}
+
 extern "C" size_t iqw_time_stats_workspace_bytes(int64_t n_channels, int64_t n_rows, int64_t n_cols,
                                                  int32_t n_stats) {
-    (void)n_channels; (void)n_stats;
+    (void)n_channels;
     if (n_cols <= 0) return 256;
-    const size_t one = carve_work(nullptr, n_cols, nullptr);
-    return n_rows >= kSampleMinRows ? 2 * one : one;
+    if (n_rows < kSampleMinRows || n_stats < 1) return carve_work(nullptr, n_cols, 0, 0, nullptr);
+    LongPlan lp{};
+    plan_long_shape(n_rows, n_cols, &lp);
+    const int groups = n_stats < kMaxGroups ? n_stats : kMaxGroups;
+    return carve_work(nullptr, n_cols, lp.splits, cap_budget(lp, groups), nullptr);
 }
 
 extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t n_rows,
@@ -991,27 +1502,13 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
     bool want_sum = false;
     if (int rc = build_plans(stats, n_stats, n_rows, &rp, &st, &want_sum)) return rc;
 
-    // sampled path?
-    RankPlan srp{};
-    BracketPlan bp{};
-    RowMap full{n_rows, 1, 0u};
-    RowMap samp = full;
-    bool sampled = false;
-    if (n_rows >= kSampleMinRows && rp.n_ranks > 0) {
-        samp.step = n_rows / kSampleRows;
-        if (samp.step < 2) samp.step = 2;
-        samp.n = n_rows / samp.step;
-        samp.seed = 0x9E3779B9u;
-        sampled = build_sample_plan(rp, n_rows, samp.n, &srp, &bp);
-    }
-
-    Work wf{}, ws{};
-    const size_t one = carve_work(d_workspace, n_cols, &wf);
-    size_t need = one;
-    if (sampled) {
-        carve_work(static_cast<char*>(d_workspace) + one, n_cols, &ws);
-        need = 2 * one;
-    }
+    // long-column (sampled, one-read) path?
+    LongPlan lp{};
+    const bool sampled = n_rows >= kSampleMinRows && rp.n_ranks > 0 &&
+                         build_long_plan(rp, n_rows, n_cols, n_stats, &lp);
+    Work w{};
+    const size_t need = sampled ? carve_work(d_workspace, n_cols, lp.splits, lp.bp.cap_sum, &w)
+                                : carve_work(d_workspace, n_cols, 0, 0, &w);
     if (workspace_bytes < need)
         return fail(IQW_ERR_WORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need);
 
@@ -1020,34 +1517,38 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
     if (int rc = device_sm_count(&sms)) return rc;
     const long long col_tiles = (n_cols + kBX - 1) / kBX;
     const unsigned cthreads = 128, cblocks = (unsigned)((n_cols + cthreads - 1) / cthreads);
+    RowMap full{n_rows, 1, 0u};
+    if (sampled)
+        IQW_CUDA_OK(cudaFuncSetAttribute(sample_brackets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSampleSmem));
 
     for (int64_t c = 0; c < n_channels; ++c) {
         const float* p = d_p + c * p_channel_stride;
         float* out = d_out + c * (int64_t)n_stats * n_cols;
-        { IQW_PROFILE("stats_init", s); if (int rc = reset_work(wf, n_cols, s)) return rc; }
+        { IQW_PROFILE("stats_init", s); if (int rc = reset_work(w, s)) return rc; }
 
         if (!sampled) {
-            if (int rc = run_exact(p, n_cols, full, rp, true, want_sum, to_dB != 0, eps, wf, sms, s, false))
+            if (int rc = run_exact(p, n_cols, full, rp, true, want_sum, to_dB != 0, eps, w, sms, s, false))
                 return rc;
         } else {
-            { IQW_PROFILE("stats_init", s); if (int rc = reset_work(ws, n_cols, s)) return rc; }
-            if (srp.n_ranks > 0)
-                if (int rc = run_exact(p, n_cols, samp, srp, false, false, false, eps, ws, sms, s, true))
-                    return rc;
+            { IQW_PROFILE("stats_sample", s);
+              sample_brackets_kernel<<<(unsigned)((n_cols + kSampleCols - 1) / kSampleCols), kSampleThreads,
+                                       kSampleSmem, s>>>(p, n_cols, lp.sample, lp.bp, w); }
+            IQW_DISPATCH_G(lp.bp.n_groups, launch_bracket_pass<M>(s, p, n_cols, n_rows, lp, want_sum, to_dB != 0, eps, w));
             { IQW_PROFILE("stats_scan", s);
-              make_brackets_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, bp, ws, wf); }
+              scan_brackets_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, n_rows, rp, lp.bp.n_groups, w); }
+            IQW_DISPATCH_G(lp.bp.n_groups, if (int rc = launch_select<M>(s, n_cols, rp, lp, w)) return rc);
+            // whatever select could not settle from the lists (missed brackets, overflowed lists,
+            // heavy ties) is refined from the matrix; these exit at once when nothing is open
             Grid g;
             if (int rc = plan_grid(n_rows, col_tiles, sms, &g)) return rc;
-            IQW_DISPATCH_M(bp.n_groups, launch_bracket<M>(g, s, p, n_cols, full, want_sum, to_dB != 0, eps, wf));
-            { IQW_PROFILE("stats_scan", s);
-              scan_bracket_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, rp, wf); }
-            IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, n_cols, full, rp, wf, cblocks, cthreads, "stats"));
-            IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, n_cols, full, wf, "stats_collect"));
+            IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, n_cols, full, rp, w, cblocks, cthreads, "stats"));
+            IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, n_cols, full, w, "stats_collect"));
             { IQW_PROFILE("stats_resolve", s);
-              resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_cols, rp, wf); }
+              resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_cols, rp, w); }
         }
         { IQW_PROFILE("stats_finalize", s);
-          finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, wf, out); }
+          finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, w, out); }
         IQW_CUDA_OK(cudaGetLastError());
     }
     return IQW_OK;

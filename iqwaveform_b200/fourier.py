@@ -176,7 +176,7 @@ def spectrogram(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, 
 
 
 def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25,
-                    out: torch.Tensor | None = None) -> torch.Tensor:
+                    out: torch.Tensor | None = None, counters: list | None = None) -> torch.Tensor:
     """statistics over axis 1 of a (C, T, nbins) float32 device tensor -> (C, nstat, nbins).
     The device-side part of fourier.py:1311-1325."""
     if p.dtype != torch.float32 or p.ndim != 3:
@@ -202,6 +202,11 @@ def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25
             _stream_ptr(p.device)))
         if sub is not out:
             out[:, g, :] = sub
+        if counters is not None:      # test aid: path counters of the last channel (synchronises)
+            c8 = (ctypes.c_uint32 * 8)()
+            _lib.check(_lib.lib.iqw_debug_time_stats_counters(ctypes.c_void_p(ws.data_ptr()), nb, c8))
+            counters.append(dict(zip(('refine', 'collect', 'missed_ranks', 'overflowed', 'select_to_collect',
+                                      'select_to_refine', 'inconsistent', 'selected'), list(c8))))
     return out
 
 
