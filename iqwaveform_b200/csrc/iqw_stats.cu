@@ -63,7 +63,7 @@ constexpr int kSampleCols = 2;     // columns per CTA of sample_brackets
 constexpr int kMaxGroups = 8;      // rank groups (brackets) per call on the sampled path
 constexpr int kSelBins = 2048;     // level-1 bins of sample_brackets and select
 constexpr int kSubBins = 256;      // level-2 sub-bins of sample_brackets
-constexpr int kSelBuf = 512;       // keys ranked in shared memory at the end of select
+constexpr int kSelBuf = 2048;      // keys ranked in shared memory at the end of select
 constexpr int kSelThreads = 512;
 constexpr int kMaxSplits = 512;    // row splits of the bracket pass (select stages their counts)
 constexpr long long kBracketCtas = 148 * 64;   // CTAs the bracket pass aims at (a few waves)
@@ -263,23 +263,27 @@ __device__ __forceinline__ uint32_t l0_bucket(uint32_t k, uint32_t lo, uint32_t 
 }
 
 // exact min / max / sum of a column (named statistics), shared by L0 and the bracket pass
-template <bool WANT_SUM, bool TO_DB>
+template <bool WANT_MINMAX, bool WANT_SUM, bool TO_DB>
 struct Named {
     uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
     double dsum = 0.0;
     float part = 0.f;
     int n_part = 0;
     __device__ __forceinline__ void add(float f, uint32_t k, float eps) {
-        kmin = min(kmin, k);
-        kmax = max(kmax, k);
+        if (WANT_MINMAX) {
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
+        }
         if (WANT_SUM) {
             part += TO_DB ? power_to_dB(f, eps) : f;
             if (++n_part == 8) { dsum += (double)part; part = 0.f; n_part = 0; }
         }
     }
     __device__ __forceinline__ void flush(const Work& w, long long col) {
-        atomicMin(w.kmin + col, kmin);
-        atomicMax(w.kmax + col, kmax);
+        if (WANT_MINMAX) {
+            atomicMin(w.kmin + col, kmin);
+            atomicMax(w.kmax + col, kmax);
+        }
         if (WANT_SUM) atomicAdd(w.dsum + col, dsum + (double)part);
     }
 };
@@ -302,7 +306,7 @@ l0_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows
     uint16_t* h = hist + threadIdx.x;
     const long long i0 = (long long)blockIdx.y * rows_per_split;
     const long long i1 = min(rm.n, i0 + rows_per_split);
-    Named<WANT_SUM, TO_DB> named;
+    Named<true, WANT_SUM, TO_DB> named;
 
     auto visit = [&](float f) {
         const uint32_t k = float_to_key(f);
@@ -608,59 +612,177 @@ refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long 
 
 // bracket pass (long-column path): the ONE read of all rows.  A thread owns a column; its M
 // brackets and 2M counters live in registers.  Per bracket it counts the keys >= lo and the keys
-// > hi (which give the keys below and inside the bracket), and every key inside ANY bracket is
-// appended to the thread's private candidate list of this row split (brackets are disjoint, so
-// the key itself says which bracket it belongs to): no atomics, no shared memory.  A full list
-// keeps counting; the overflow is flagged and the column is refined from the matrix instead.
-template <int M, bool WANT_SUM, bool TO_DB>
-__global__ void __launch_bounds__(kBX)
-bracket_pass_kernel(const float* __restrict__ p, long long cols, long long rows,
-                    long long rows_per_split, float eps, BracketPlan bp, Work w) {
-    const long long col = (long long)blockIdx.x * kBX + threadIdx.x;
-    if (col >= cols) return;
-    uint32_t lo[M], hi[M], n_ge[M], n_gt[M];
+// inside [lo, hi] (which give the keys below and inside the bracket), and every key inside ANY
+// bracket is appended to the thread's private candidate list of this row split (brackets are
+// disjoint, so the key itself says which bracket it belongs to): no atomics, no shared memory.
+// A full list keeps counting; the overflow is flagged and the column is refined from the matrix.
+//
+// The per-element body is inline PTX (bracket_visit.inc, 4M + 7 instructions for M brackets).
+// RAW mode compares the raw float bits as signed integers instead of order-preserving keys, which
+// is exact when every bracket bound is a non-negative float or an open end (always the case for
+// power spectra) and saves the key conversion; the lists then hold raw bits.  Flag pending[8],
+// set by sample_brackets when it sees a negative bound, selects the mode for the whole call.
+#include "bracket_visit.inc"
+
+// generic (M = 8) body in C++
+template <bool RAW, int M>
+__device__ __forceinline__ void bracket_visit_generic(uint32_t v, float (&nge)[M], float (&nin)[M],
+                                                      uint32_t& slot, const uint32_t (&lo)[M],
+                                                      const uint32_t (&hi)[M]) {
+    bool inside = false;
 #pragma unroll
     for (int g = 0; g < M; ++g) {
-        lo[g] = w.bk_lo[col * kMaxGroups + g];
-        hi[g] = w.bk_hi[col * kMaxGroups + g];
-        n_ge[g] = 0; n_gt[g] = 0;
+        const bool ge = RAW ? (int32_t)v >= (int32_t)lo[g] : v >= lo[g];
+        const bool in = ge && (RAW ? (int32_t)v <= (int32_t)hi[g] : v <= hi[g]);
+        nge[g] += ge ? 1.f : 0.f;
+        nin[g] += in ? 1.f : 0.f;
+        inside |= in;
     }
-    const uint32_t cap = bp.cap_sum;
-    uint32_t* __restrict__ list = w.lists + ((long long)blockIdx.y * cols + col) * (long long)cap;
-    uint32_t n_list = 0;
-    const long long i0 = (long long)blockIdx.y * rows_per_split;
-    const long long i1 = min(rows, i0 + rows_per_split);
-    Named<WANT_SUM, TO_DB> named;
-    auto visit = [&](float f) {
-        const uint32_t k = float_to_key(f);
-        named.add(f, k, eps);
-        bool inside = false;
+    if (inside) {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(v) : "memory");
+        slot += 4;
+    }
+}
+
+// Candidate appends go through a per-thread staging buffer of kStage keys in shared memory.  After
+// every kUnroll rows, a buffer holding >= 32 keys is drained: the whole warp writes its first 32
+// keys as ONE aligned 128-byte line of the owner's list, and the owner moves the (< kUnroll) keys
+// that are left to the front.  (Appending with scattered 4-byte stores costs ~9 ps each chip-wide
+// -- partial-sector writes -- which was 60 % of this kernel's time; tools/exp/exp_colstream.cu.)
+constexpr int kLine = 32;                       // keys per 128-byte line
+constexpr int kStage = kLine + kUnroll;         // most keys a buffer can hold between drains
+constexpr int kStagePitch = kStage + 1;         // odd pitch: a warp reads one buffer conflict-free
+
+template <int M, int NAMED /* bit 0: min/max, bit 1: sum, bit 2: sum of dB */, bool RAW>
+__device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, long long cols, long long col,
+                                                  bool live_col, long long i0, long long i1, float eps,
+                                                  const BracketPlan& bp, const Work& w, uint32_t* stage) {
+    uint32_t lo[M], hi[M];
+    float n_ge[M], n_in[M];      // float counters: exact (rows per split < 2^24), FMA-pipe adds
 #pragma unroll
-        for (int g = 0; g < M; ++g) {
-            const bool ge = k >= lo[g], gt = k > hi[g];
-            n_ge[g] += ge ? 1u : 0u;
-            n_gt[g] += gt ? 1u : 0u;
-            inside |= ge && !gt;
+    for (int g = 0; g < M; ++g) {
+        // a thread past the last column streams the last column but owns empty brackets
+        lo[g] = (live_col ? w.bk_lo[col * kMaxGroups + g] : 0xFFFFFFFFu) ^ (RAW ? 0x80000000u : 0u);
+        hi[g] = (live_col ? w.bk_hi[col * kMaxGroups + g] : 0u) ^ (RAW ? 0x80000000u : 0u);
+        n_ge[g] = 0.f; n_in[g] = 0.f;
+    }
+    const uint32_t cap = bp.cap_sum;                    // multiple of kLine
+    const int lane = threadIdx.x & 31;
+    uint32_t* my_stage = stage + threadIdx.x * kStagePitch;
+    const uint32_t* warp_stage = stage + (threadIdx.x - lane) * kStagePitch;
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(my_stage);
+    uint32_t slot = stage_addr;                         // shared address of the next free entry
+    uint32_t n_lines = 0;                               // lines this thread's list received so far
+    // list of lane 0's column in this row split; lists of adjacent columns are `cap` keys apart.
+    // (computed from the unclamped thread index: a thread past the last column never appends)
+    uint32_t* warp_list = w.lists + ((long long)blockIdx.y * cols + (long long)blockIdx.x * kBX +
+                                     (threadIdx.x - lane)) * (long long)cap;
+    Named<(NAMED & 1) != 0, (NAMED & 2) != 0, (NAMED & 4) != 0> named;
+
+    auto drain = [&](bool ready) {
+        unsigned m = __ballot_sync(0xFFFFFFFFu, ready);
+        __syncwarp();                       // the owners' appends are visible to the warp
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t start = __shfl_sync(0xFFFFFFFFu, n_lines, src) * kLine;
+            if (start + kLine <= cap)
+                warp_list[(uint32_t)src * cap + start + lane] = warp_stage[src * kStagePitch + lane];
         }
-        if (inside) {
-            if (n_list < cap) list[n_list] = k;
-            ++n_list;
+        __syncwarp();                       // buffers are read before their owners touch them again
+        if (ready) {
+            // move the (< kUnroll) keys behind the line to the front: independent loads first
+            const uint32_t left = (slot - stage_addr) / 4 - kLine;
+            uint32_t t[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) t[j] = my_stage[kLine + j];
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j)
+                if ((uint32_t)j < left) my_stage[j] = t[j];
+            slot -= kLine * 4;
+            ++n_lines;
         }
     };
-    RowMap all{rows, 1, 0u};
-    stream_column<false>(p, cols, col, all, i0, i1, visit);
+    auto visit = [&](float f) {
+        const uint32_t bits = __float_as_uint(f);
+        if (NAMED) named.add(f, float_to_key(f), eps);
+        const uint32_t v = RAW ? bits : float_to_key(f);
+        if constexpr (M <= 4) bracket_visit<RAW>(v, n_ge, n_in, slot, lo, hi);
+        else bracket_visit_generic<RAW, M>(v, n_ge, n_in, slot, lo, hi);
+    };
+    // rows i0..i1 of this column; software-pipelined: the loads of the next kUnroll rows are in
+    // flight while the current ones are classified
+    const float* src = p + i0 * cols + col;
+    long long i = i0;
+    float f[kUnroll];
+    if (i + kUnroll <= i1) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u, src += cols) f[u] = __ldcs(src);
+    }
+#pragma unroll 1
+    for (; i + kUnroll <= i1; i += kUnroll) {
+        float nx[kUnroll];
+        const bool more = i + 2 * kUnroll <= i1;
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u, src += cols) nx[u] = __ldcs(src);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) visit(f[u]);
+        const bool ready = slot - stage_addr >= kLine * 4;
+        if (__any_sync(0xFFFFFFFFu, ready)) drain(ready);
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) f[u] = nx[u];
+        }
+    }
+#pragma unroll 1
+    for (; i < i1; ++i, src += cols) {      // < kUnroll rows: the buffer cannot overflow
+        visit(__ldcs(src));
+    }
+    {
+        const bool ready = slot - stage_addr >= kLine * 4;
+        if (__any_sync(0xFFFFFFFFu, ready)) drain(ready);
+    }
+    // what is left (< 32 keys per thread)
+    const uint32_t rem_mine = (slot - stage_addr) / 4;
+    __syncwarp();
+    for (int s = 0; s < 32; ++s) {
+        const uint32_t rem = __shfl_sync(0xFFFFFFFFu, rem_mine, s);
+        const uint32_t start = __shfl_sync(0xFFFFFFFFu, n_lines, s) * kLine;
+        if ((uint32_t)lane < rem && start + kLine <= cap)
+            warp_list[(uint32_t)s * cap + start + lane] = warp_stage[s * kStagePitch + lane];
+    }
+    if (!live_col) return;
 
     const uint32_t n = (uint32_t)(i1 > i0 ? i1 - i0 : 0);
 #pragma unroll
     for (int g = 0; g < M; ++g) {
-        if (g < bp.n_groups && lo[g] <= hi[g]) {
-            if (n - n_ge[g]) atomicAdd(w.t_below + col * kMaxGroups + g, n - n_ge[g]);
-            if (n_ge[g] - n_gt[g]) atomicAdd(w.t_cnt + col * kMaxGroups + g, n_ge[g] - n_gt[g]);
+        const bool live = RAW ? (int32_t)lo[g] <= (int32_t)hi[g] : lo[g] <= hi[g];
+        if (g < bp.n_groups && live) {
+            const uint32_t ge = (uint32_t)n_ge[g], in = (uint32_t)n_in[g];
+            if (n - ge) atomicAdd(w.t_below + col * kMaxGroups + g, n - ge);
+            if (in) atomicAdd(w.t_cnt + col * kMaxGroups + g, in);
         }
     }
+    const uint32_t n_list = n_lines * kLine + rem_mine;
     w.s_cnt[(long long)blockIdx.y * cols + col] = min(n_list, cap);
     if (n_list > cap) atomicOr(w.t_ovf + col, 1u);
     named.flush(w, col);
+}
+
+template <int M, int NAMED>
+__global__ void __launch_bounds__(kBX)
+bracket_pass_kernel(const float* __restrict__ p, long long cols, long long rows,
+                    long long rows_per_split, float eps, BracketPlan bp, Work w) {
+    __shared__ uint32_t stage[kBX * kStagePitch];
+    long long col = (long long)blockIdx.x * kBX + threadIdx.x;
+    const bool live_col = col < cols;
+    if (!live_col) col = cols - 1;          // keep the warp whole: it flushes rings cooperatively
+    const long long i0 = (long long)blockIdx.y * rows_per_split;
+    const long long i1 = min(rows, i0 + rows_per_split);
+    if (w.pending[8] == 0) bracket_pass_body<M, NAMED, true>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
+    else bracket_pass_body<M, NAMED, false>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
 }
 
 template <int M>
@@ -923,6 +1045,8 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
             }
             w.bk_lo[col * kMaxGroups + g] = lo;
             w.bk_hi[col * kMaxGroups + g] = hi;
+            // a bound that is a negative float (other than the open low end) rules out RAW mode
+            if (lo <= hi && ((lo != 0u && lo < 0x80000000u) || hi < 0x80000000u)) atomicOr(w.pending + 8, 1u);
         }
     }
 }
@@ -977,6 +1101,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     for (int i = t; i < splits; i += kSelThreads) cnts[i] = w.s_cnt[(long long)i * cols + col];
 
     const uint32_t cap_sum = bp.cap_sum;
+    const bool raw = w.pending[8] == 0;     // lists hold raw float bits (bracket pass RAW mode)
     // bracket of a key among those in `mode` (brackets are disjoint), -1 if none
     auto bracket_of = [&](uint32_t k, uint32_t mode) {
         int g = -1;
@@ -999,7 +1124,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                    if (i0 + u * 32 + lane < n) visit(k[u]);
+                    if (i0 + u * 32 + lane < n) visit(raw ? float_to_key(__uint_as_float(k[u])) : k[u]);
             }
         }
     };
@@ -1251,6 +1376,7 @@ static void plan_long_shape(int64_t rows, int64_t cols, LongPlan* lp) {
     if (splits > kMaxSplits) splits = kMaxSplits;
     long long rps = (rows + splits - 1) / splits;
     if (rps < kMinRowsPerSplit) rps = kMinRowsPerSplit;
+    // rps <= rows / 512 + 1 < 2^23 + 1 for rows < 2^32: the bracket pass counts rows in floats
     lp->rows_per_split = rps;
     lp->splits = (rows + rps - 1) / rps;
     long long step = (rows + kSampleRows - 1) / kSampleRows;
@@ -1267,7 +1393,8 @@ static long long max_group_width(long long srows) {
 static long long cap_budget(const LongPlan& lp, int n_groups) {
     double f = (double)n_groups * (double)(max_group_width(lp.sample.n) + 2) / (double)lp.sample.n;
     if (f > 1.0) f = 1.0;
-    return (long long)std::ceil(1.5 * (double)lp.rows_per_split * f) + 32ll * n_groups;
+    const long long cap = (long long)std::ceil(1.5 * (double)lp.rows_per_split * f) + 32ll * n_groups;
+    return (cap + kLine - 1) / kLine * kLine;            // whole 128-byte lines
 }
 
 // Returns false when the sampled path does not apply (too many groups).
@@ -1317,7 +1444,8 @@ static bool build_long_plan(const RankPlan& rp, int64_t rows, int64_t cols, int 
     long long cap = (long long)std::ceil(1.5 * (double)lp->rows_per_split * share) + 32ll * ng;
     const long long budget = cap_budget(*lp, n_stats < kMaxGroups ? n_stats : kMaxGroups);
     if (cap > budget) cap = budget;
-    bp.cap_sum = (unsigned)cap;
+    bp.cap_sum = (unsigned)(cap / kLine * kLine);       // whole 128-byte lines
+    if (bp.cap_sum == 0) bp.cap_sum = kLine;
     return true;
 }
 
@@ -1369,15 +1497,21 @@ static void launch_collect(const Grid& g, cudaStream_t s, const float* p, long l
 
 template <int M>
 static void launch_bracket_pass(cudaStream_t s, const float* p, long long cols, long long rows,
-                                const LongPlan& lp, bool want_sum, bool to_dB, float eps, const Work& w) {
+                                const LongPlan& lp, bool want_minmax, bool want_sum, bool to_dB, float eps,
+                                const Work& w) {
     const dim3 grid((unsigned)((cols + kBX - 1) / kBX), (unsigned)lp.splits);
     IQW_PROFILE("stats_bracket_pass", s);
-    if (want_sum && to_dB)
-        bracket_pass_kernel<M, true, true><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w);
-    else if (want_sum)
-        bracket_pass_kernel<M, true, false><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w);
-    else
-        bracket_pass_kernel<M, false, false><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w);
+#define IQW_BP(N) bracket_pass_kernel<M, N><<<grid, kBX, 0, s>>>(p, cols, rows, lp.rows_per_split, eps, lp.bp, w)
+    const int named = (want_minmax ? 1 : 0) | (want_sum ? 2 : 0) | (want_sum && to_dB ? 4 : 0);
+    switch (named) {
+        case 0: IQW_BP(0); break;
+        case 1: IQW_BP(1); break;
+        case 2: IQW_BP(2); break;
+        case 3: IQW_BP(3); break;
+        case 6: IQW_BP(6); break;
+        default: IQW_BP(7); break;
+    }
+#undef IQW_BP
 }
 
 template <int M>
@@ -1499,8 +1633,11 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
 
     RankPlan rp{};
     StatPlan st{};
-    bool want_sum = false;
+    bool want_sum = false, want_minmax = false;
     if (int rc = build_plans(stats, n_stats, n_rows, &rp, &st, &want_sum)) return rc;
+    for (int i = 0; i < n_stats; ++i)
+        want_minmax |= stats[i].kind == IQW_STAT_MAX || stats[i].kind == IQW_STAT_MIN;
+    if (n_cols >= (1ll << 27)) return fail(IQW_ERR_UNSUPPORTED, "n_cols >= 2^27");
 
     // long-column (sampled, one-read) path?
     LongPlan lp{};
@@ -1534,7 +1671,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
             { IQW_PROFILE("stats_sample", s);
               sample_brackets_kernel<<<(unsigned)((n_cols + kSampleCols - 1) / kSampleCols), kSampleThreads,
                                        kSampleSmem, s>>>(p, n_cols, lp.sample, lp.bp, w); }
-            IQW_DISPATCH_G(lp.bp.n_groups, launch_bracket_pass<M>(s, p, n_cols, n_rows, lp, want_sum, to_dB != 0, eps, w));
+            IQW_DISPATCH_G(lp.bp.n_groups, launch_bracket_pass<M>(s, p, n_cols, n_rows, lp, want_minmax, want_sum, to_dB != 0, eps, w));
             { IQW_PROFILE("stats_scan", s);
               scan_brackets_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, n_rows, rp, lp.bp.n_groups, w); }
             IQW_DISPATCH_G(lp.bp.n_groups, if (int rc = launch_select<M>(s, n_cols, rp, lp, w)) return rc);

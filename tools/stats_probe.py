@@ -10,7 +10,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
 x = bench.device_capture(torch, n, 1234, dev).view(1, n)
 _, _, p = iqw.spectrogram(x, fs=100e6, window='hann', nperseg=4096, noverlap=2048, axis=1)
 print('spectrogram', tuple(p.shape))
-for stats in ([0.1, 0.5, 0.9, 0.999], [0.5], [0.5, 0.99, 'mean', 'max']):
+ALL = ([0.1, 0.5, 0.9, 0.999], [0.5], [0.5, 0.99, 'mean', 'max'])
+sel = [ALL[int(a)] for a in sys.argv[2:]] or ALL
+for stats in sel:
     cnt = []
     out = iqw.time_statistics(p, stats, dB=True, counters=cnt)
     torch.cuda.synchronize()
