@@ -10,12 +10,12 @@ Importing the package loads ``libiqw_b200.so`` and fails loudly when it is missi
 CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is absent)
-from . import fourier, power_analysis
+from . import fourier, power_analysis, distributed
 from .fourier import (stft, spectrogram, power_spectral_density, persistence_spectrum, fftfreq,
                       get_window, equivalent_noise_bandwidth, time_statistics)
 from .power_analysis import iq_to_bin_power
 
 __version__ = '0.1.0'
-__all__ = ['fourier', 'power_analysis', 'stft', 'spectrogram', 'power_spectral_density',
+__all__ = ['fourier', 'power_analysis', 'distributed', 'stft', 'spectrogram', 'power_spectral_density',
            'persistence_spectrum', 'fftfreq', 'get_window', 'equivalent_noise_bandwidth',
            'time_statistics', 'iq_to_bin_power']

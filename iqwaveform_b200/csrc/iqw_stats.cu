@@ -628,7 +628,7 @@ refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long 
 template <bool RAW, int M>
 __device__ __forceinline__ void bracket_visit_generic(uint32_t v, float (&nge)[M], float (&nin)[M],
                                                       uint32_t& slot, const uint32_t (&lo)[M],
-                                                      const uint32_t (&hi)[M]) {
+                                                      const uint32_t (&hi)[M], uint32_t base) {
     bool inside = false;
 #pragma unroll
     for (int g = 0; g < M; ++g) {
@@ -639,8 +639,8 @@ __device__ __forceinline__ void bracket_visit_generic(uint32_t v, float (&nge)[M
         inside |= in;
     }
     if (inside) {
-        asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(v) : "memory");
-        slot += 4;
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + 4 * slot), "r"(v) : "memory");
+        slot += 1;
     }
 }
 
@@ -671,7 +671,7 @@ __device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, l
     uint32_t* my_stage = stage + threadIdx.x * kStagePitch;
     const uint32_t* warp_stage = stage + (threadIdx.x - lane) * kStagePitch;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(my_stage);
-    uint32_t slot = stage_addr;                         // shared address of the next free entry
+    uint32_t slot = 0;                                  // keys in the staging buffer
     uint32_t n_lines = 0;                               // lines this thread's list received so far
     // list of lane 0's column in this row split; lists of adjacent columns are `cap` keys apart.
     // (computed from the unclamped thread index: a thread past the last column never appends)
@@ -692,14 +692,14 @@ __device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, l
         __syncwarp();                       // buffers are read before their owners touch them again
         if (ready) {
             // move the (< kUnroll) keys behind the line to the front: independent loads first
-            const uint32_t left = (slot - stage_addr) / 4 - kLine;
+            const uint32_t left = slot - kLine;
             uint32_t t[kUnroll];
 #pragma unroll
             for (int j = 0; j < kUnroll; ++j) t[j] = my_stage[kLine + j];
 #pragma unroll
             for (int j = 0; j < kUnroll; ++j)
                 if ((uint32_t)j < left) my_stage[j] = t[j];
-            slot -= kLine * 4;
+            slot -= kLine;
             ++n_lines;
         }
     };
@@ -707,45 +707,45 @@ __device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, l
         const uint32_t bits = __float_as_uint(f);
         if (NAMED) named.add(f, float_to_key(f), eps);
         const uint32_t v = RAW ? bits : float_to_key(f);
-        if constexpr (M <= 4) bracket_visit<RAW>(v, n_ge, n_in, slot, lo, hi);
-        else bracket_visit_generic<RAW, M>(v, n_ge, n_in, slot, lo, hi);
+        if constexpr (M <= 4) bracket_visit<RAW>(v, n_ge, n_in, slot, lo, hi, stage_addr);
+        else bracket_visit_generic<RAW, M>(v, n_ge, n_in, slot, lo, hi, stage_addr);
     };
-    // rows i0..i1 of this column; software-pipelined: the loads of the next kUnroll rows are in
-    // flight while the current ones are classified
+    // rows i0..i1 of this column; software-pipelined with two register buffers: the loads of the
+    // next kUnroll rows are in flight while the current ones are classified
     const float* src = p + i0 * cols + col;
     long long i = i0;
-    float f[kUnroll];
-    if (i + kUnroll <= i1) {
+    float fa[kUnroll], fb[kUnroll];
+    auto load_block = [&](float (&f)[kUnroll]) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u, src += cols) f[u] = __ldcs(src);
-    }
-#pragma unroll 1
-    for (; i + kUnroll <= i1; i += kUnroll) {
-        float nx[kUnroll];
-        const bool more = i + 2 * kUnroll <= i1;
-        if (more) {
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u, src += cols) nx[u] = __ldcs(src);
-        }
+    };
+    auto visit_block = [&](float (&f)[kUnroll]) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) visit(f[u]);
-        const bool ready = slot - stage_addr >= kLine * 4;
+        const bool ready = slot >= kLine;
         if (__any_sync(0xFFFFFFFFu, ready)) drain(ready);
-        if (more) {
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) f[u] = nx[u];
-        }
+    };
+    if (i + kUnroll <= i1) load_block(fa);
+#pragma unroll 1
+    while (i + kUnroll <= i1) {
+        if (i + 2 * kUnroll <= i1) load_block(fb);
+        visit_block(fa);
+        i += kUnroll;
+        if (i + kUnroll > i1) break;
+        if (i + 2 * kUnroll <= i1) load_block(fa);
+        visit_block(fb);
+        i += kUnroll;
     }
 #pragma unroll 1
     for (; i < i1; ++i, src += cols) {      // < kUnroll rows: the buffer cannot overflow
         visit(__ldcs(src));
     }
     {
-        const bool ready = slot - stage_addr >= kLine * 4;
+        const bool ready = slot >= kLine;
         if (__any_sync(0xFFFFFFFFu, ready)) drain(ready);
     }
     // what is left (< 32 keys per thread)
-    const uint32_t rem_mine = (slot - stage_addr) / 4;
+    const uint32_t rem_mine = slot;
     __syncwarp();
     for (int s = 0; s < 32; ++s) {
         const uint32_t rem = __shfl_sync(0xFFFFFFFFu, rem_mine, s);

@@ -59,9 +59,35 @@ __global__ void __launch_bounds__(BX) k_store(const float* __restrict__ p, long 
             if (MODE == 0) { if (in) { if (nl < cap) list[nl] = v; ++nl; } }
             if (MODE == 1) { if (in) { if (nl < cap) __stcs(list + nl, v); ++nl; } }
             if (MODE == 2) { if (in) ++nl; }      // count only
+            if (MODE == 3) { if (in) ++nl; }
         }
     }
     atomicAdd(out + (col & 1023), acc + nl);
+}
+
+// variant: count + the warp writes one full 128-byte line every `period` rows (what drained staging buffers cost)
+template <int BX, int U>
+__global__ void __launch_bounds__(BX) k_line(const float* __restrict__ p, long long cols, long long rows,
+                                             long long rps, unsigned* out, unsigned* lists, int period) {
+    const long long col = (long long)blockIdx.x * BX + threadIdx.x;
+    if (col >= cols) return;
+    const long long i0 = (long long)blockIdx.y * rps;
+    const long long i1 = min(rows, i0 + rps);
+    const float* src = p + i0 * cols + col;
+    unsigned* line = lists + ((long long)blockIdx.y * cols + (col & ~31ll)) * 64 + (threadIdx.x & 31);
+    unsigned acc = 0; int k = 0;
+    long long i = i0;
+#pragma unroll 1
+    for (; i + U <= i1; i += U) {
+        float f[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u, src += cols) f[u] = __ldcs(src);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += __float_as_uint(f[u]) >= 0x3a000000u;
+        k += U;
+        if (k >= period) { k -= period; *line = acc; line += 32; }
+    }
+    atomicAdd(out + (col & 1023), acc);
 }
 
 // variant: each thread owns 4 adjacent columns (128-bit loads)
@@ -140,11 +166,11 @@ void run4(const float* p, long long cols, long long rows, long long ctas_target,
 }
 
 int main() {
-    const long long cols = 4096, rows = 262144;   // 4.3 GB
+    const long long cols = 4096, rows = 488280;   // 8 GB
     float* p; unsigned* out;
     cudaMalloc(&p, rows * cols * 4); cudaMalloc(&out, 4096);
     fill<<<2048, 256>>>(p, rows * cols); cudaDeviceSynchronize();
-    for (long long ctas : {148ll * 16, 148ll * 64, 148ll * 256}) {
+    for (long long ctas : {148ll * 64}) {
         run<128, 8, 1>(p, cols, rows, ctas, out);
         run<128, 16, 1>(p, cols, rows, ctas, out);
         run<256, 8, 1>(p, cols, rows, ctas, out);
@@ -158,12 +184,18 @@ int main() {
         run4<1024, 4>(p, cols, rows, ctas, out);
     }
     unsigned* lists; cudaMalloc(&lists, (size_t)rows * cols * 4);
-    for (float frac : {0.067f, 0.155f, 0.3f}) {
+    for (float frac : {0.067f}) {
         runs<128, 8, 0>(p, cols, rows, 148 * 64, out, lists, frac);
         runs<128, 8, 1>(p, cols, rows, 148 * 64, out, lists, frac);
         runs<128, 8, 2>(p, cols, rows, 148 * 64, out, lists, frac);
         runs<128, 8, 0>(p, cols, rows, 148 * 16, out, lists, frac);
         runs<1024, 8, 0>(p, cols, rows, 148 * 64, out, lists, frac);
+    }
+    for (int period : {1 << 30, 64, 32, 16, 8}) {
+        const long long tiles = cols / 128; long long splits = 148 * 64 / tiles; long long rps = (rows + splits - 1) / splits; splits = (rows + rps - 1) / rps;
+        dim3 grid((unsigned)tiles, (unsigned)splits);
+        float ms = time_it([&] { k_line<128, 8><<<grid, 128>>>(p, cols, rows, rps, out, lists, period); });
+        printf("LINE period=%d rps=%lld: %.3f ms  %.0f GB/s read, write %.2f GB\n", period, rps, ms, rows * cols * 4.0 / ms / 1e6, rows * cols * 4.0 / period / 1e9);
     }
     for (int w : {2, 4, 8}) {
         if (w == 2) { run<128, 8, 2>(p, cols, rows, 148 * 64, out); run<1024, 8, 2>(p, cols, rows, 148 * 64, out); }
