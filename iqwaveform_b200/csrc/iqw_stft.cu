@@ -105,25 +105,34 @@ stft_kernel(const StftArgs a) {
     const int nbins = a.bin_hi - a.bin_lo;
     int par = 0;
 
+    // software pipeline: the samples of the NEXT frame group are loaded into registers while the
+    // current one is transformed (they are only multiplied by the window when their turn comes)
+    float2 nx[E];
+    auto prefetch = [&](long long g) {
+        const long long c = g / a.groups_per_ch;
+        const long long frame = (g - c * a.groups_per_ch) * FPC + slot;
+        if (g < g_end && frame < a.n_frames) {
+            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
+#pragma unroll
+            for (int q = 0; q < E / R0; ++q)
+#pragma unroll
+                for (int r = 0; r < R0; ++r) nx[q * R0 + r] = __ldg(src + q * TPF + r * (N / R0));
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) nx[e] = make_float2(0.f, 0.f);
+        }
+    };
+    prefetch(g_begin);
+
     for (long long g = g_begin; g < g_end; ++g) {
         const long long c = g / a.groups_per_ch;
         const long long frame = (g - c * a.groups_per_ch) * FPC + slot;
         const bool valid = frame < a.n_frames;
 
         float2 v[E];
-        if (valid) {
-            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
 #pragma unroll
-            for (int q = 0; q < E / R0; ++q)
-#pragma unroll
-                for (int r = 0; r < R0; ++r) {
-                    float2 s = __ldg(src + q * TPF + r * (N / R0));
-                    v[q * R0 + r] = make_float2(s.x * w[q * R0 + r], s.y * w[q * R0 + r]);
-                }
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = make_float2(0.f, 0.f);
-        }
+        for (int e = 0; e < E; ++e) v[e] = make_float2(nx[e].x * w[e], nx[e].y * w[e]);
+        prefetch(g + 1);
 
         PassLoop<LOG2N, 0>::run(v, bufs, tw, ltid, slot, par);
 
