@@ -186,10 +186,31 @@ IQW_HD void bfly(float2* a) {
 // element r of butterfly q in v[q*R + r].
 //   FIRST: v was filled by the caller from global memory (windowed samples), no twiddle
 //   LAST : v is left in registers for the caller's epilogue; bin of v[q*R + r] is j + r*N/R
-// `src`/`dst` are this frame's ping-pong exchange buffers (padded), `tw` the whole twiddle table.
+// `src`/`dst` are this frame's ping-pong exchange buffers (padded), `t` the thread's twiddles of
+// this pass (load_twiddles).
 // ------------------------------------------------------------------------------------------
+// twiddles of pass P (>= 1) for this thread: t[q*(R-1) + r-1] = W_{Ns*R}^{r*(j mod Ns)}.  Loaded
+// separately from the pass so that the caller can issue the loads BEFORE the barrier that
+// precedes the pass (they do not depend on the exchanged data).
 template <int LOG2N, int P>
-IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* tw, int ltid) {
+IQW_HD void load_twiddles(float2* t, const float2* tw, int ltid) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int E = plan_elems(LOG2N);
+    constexpr int TPF = N / E;
+    constexpr int R = plan_radix(LOG2N, P);
+    constexpr int Ns = plan_ns(LOG2N, P);
+    constexpr int NB = E / R;
+    constexpr int TWO = plan_tw_offset(LOG2N, P);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int i = (ltid + q * TPF) & (Ns - 1);
+#pragma unroll
+        for (int r = 1; r < R; ++r) t[q * (R - 1) + r - 1] = tw[TWO + (r - 1) * Ns + i];
+    }
+}
+
+template <int LOG2N, int P>
+IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* t, int ltid) {
     constexpr int N = 1 << LOG2N;
     constexpr int E = plan_elems(LOG2N);
     constexpr int TPF = N / E;
@@ -198,7 +219,6 @@ IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* tw
     constexpr int NB = E / R;
     constexpr bool FIRST = (P == 0);
     constexpr bool LAST = (P == plan_passes(LOG2N) - 1);
-    constexpr int TWO = plan_tw_offset(LOG2N, P);
 
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
@@ -212,9 +232,8 @@ IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* tw
                 else
                     a[r] = src[pad_index(j + r * (N / R))];
             }
-            const int i = j & (Ns - 1);
 #pragma unroll
-            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], tw[TWO + (r - 1) * Ns + i]);
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], t[q * (R - 1) + r - 1]);
         }
         bfly<R, 1>(a);
         if constexpr (!LAST) {

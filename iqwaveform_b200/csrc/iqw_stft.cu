@@ -56,18 +56,22 @@ struct StftCfg {
 
 template <int LOG2N, int P>
 struct PassLoop {
-    // runs passes P..NP-1; `par` selects the ping-pong buffer the NEXT exchange writes
-    static __device__ __forceinline__ void run(float2* v, float2* bufs, const float2* tw, int ltid,
-                                               int slot, int& par) {
+    // runs passes P..NP-1; `par` selects the ping-pong buffer the NEXT exchange writes.  The
+    // twiddles of pass P+1 are fetched before the barrier that separates it from pass P.
+    static __device__ __forceinline__ void run(float2* v, float2* bufs, const float2* tw, const float2* t,
+                                               int ltid, int slot, int& par) {
         using C = StftCfg<LOG2N>;
         constexpr bool LAST = (P == C::NP - 1);
         float2* wr = bufs + ((size_t)par * C::FPC + slot) * C::PADN;
         const float2* rd = bufs + ((size_t)(par ^ 1) * C::FPC + slot) * C::PADN;
-        fft_pass<LOG2N, P>(v, rd, wr, tw, ltid);
+        fft_pass<LOG2N, P>(v, rd, wr, t, ltid);
         if constexpr (!LAST) {
+            constexpr int E = plan_elems(LOG2N);
+            float2 tn[E];
+            load_twiddles<LOG2N, P + 1>(tn, tw, ltid);
             __syncthreads();
             par ^= 1;
-            PassLoop<LOG2N, P + 1>::run(v, bufs, tw, ltid, slot, par);
+            PassLoop<LOG2N, P + 1>::run(v, bufs, tw, tn, ltid, slot, par);
         }
     }
 };
@@ -134,7 +138,7 @@ stft_kernel(const StftArgs a) {
         for (int e = 0; e < E; ++e) v[e] = make_float2(nx[e].x * w[e], nx[e].y * w[e]);
         prefetch(g + 1);
 
-        PassLoop<LOG2N, 0>::run(v, bufs, tw, ltid, slot, par);
+        PassLoop<LOG2N, 0>::run(v, bufs, tw, nullptr, ltid, slot, par);
 
         if (valid) {
             const long long row = c * a.out_ch_stride + frame * (long long)nbins - a.bin_lo;

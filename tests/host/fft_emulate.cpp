@@ -16,8 +16,11 @@ struct Runner {
     static void run(std::vector<float2>& regs, std::vector<float2>& a, std::vector<float2>& b,
                     const std::vector<float2>& tw) {
         constexpr int N = 1 << LOG2N, E = plan_elems(LOG2N), TPF = N / E;
-        for (int t = 0; t < TPF; ++t)
-            fft_pass<LOG2N, P>(&regs[t * E], a.data(), b.data(), tw.data(), t);
+        for (int t = 0; t < TPF; ++t) {
+            float2 tn[E];
+            if constexpr (P > 0) load_twiddles<LOG2N, P>(tn, tw.data(), t);
+            fft_pass<LOG2N, P>(&regs[t * E], a.data(), b.data(), tn, t);
+        }
         if constexpr (P + 1 < plan_passes(LOG2N)) Runner<LOG2N, P + 1>::run(regs, b, a, tw);
     }
 };
