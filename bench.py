@@ -130,7 +130,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                  '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -231,12 +231,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # clocks under load: warm-up + timed region
     for _ in range(warmup):
         step(x)
     barrier()
 
     # ---- device-resident timed region --------------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     _lib.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -341,7 +341,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--samples', type=int, default=SAMPLES_PER_CHANNEL,

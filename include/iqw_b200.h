@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IQW_ABI_VERSION 1
+#define IQW_ABI_VERSION 2
 
 typedef enum iqw_status {
     IQW_OK = 0,
@@ -74,17 +74,23 @@ const char* iqw_last_error(void);
  *   d_window      nfft float32 coefficients that multiply a frame.  The caller folds in the
  *                 (-1)^n fft-shift, the 1/nfft and (norm=None) the COLA scale, exactly as the
  *                 reference does on the host (fourier.py:1002-1010, 1033, 571-580)
- *   nfft          power of two, 16 <= nfft <= 8192 (larger: IQW_ERR_UNSUPPORTED)
+ *   nfft          power of two, 16 <= nfft <= 65536 (others: IQW_ERR_UNSUPPORTED).  Up to 8192 a
+ *                 frame is transformed inside one CTA's shared memory; 16384..65536 run as a
+ *                 two-kernel four-step FFT through d_workspace
  *   hop           nfft - noverlap >= 1;  frame m covers samples [m*hop, m*hop + nfft)
  *   n_frames      T <= (n_samples - nfft)/hop + 1
  *   bin_lo,bin_hi output bins [bin_lo, bin_hi) of the fft-shifted spectrum (0, nfft = all)
  *   d_out         (n_channels, n_frames, bin_hi-bin_lo), complex64 (COMPLEX) or float32,
  *                 C-contiguous, channel stride out_channel_stride elements
+ *   d_workspace   >= iqw_stft_workspace_bytes(nfft, n_channels, n_frames) bytes, 16-byte aligned;
+ *                 may be NULL when that is 0 (nfft <= 8192).  Any size >= one frame (8*nfft bytes)
+ *                 works: frames are processed in chunks that fit
  */
+size_t iqw_stft_workspace_bytes(int32_t nfft, int64_t n_channels, int64_t n_frames);
 int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,
                  const float* d_window, int32_t nfft, int64_t hop, int64_t n_frames, int32_t mode,
                  float eps, int32_t bin_lo, int32_t bin_hi, void* d_out,
-                 int64_t out_channel_stride, void* stream);
+                 int64_t out_channel_stride, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 2: statistics over the time axis of a (n_channels, n_rows, n_cols) float32 matrix

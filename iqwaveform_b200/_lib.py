@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libiqw_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # statuses / enums mirrored from include/iqw_b200.h
 IQW_OK = 0
@@ -44,8 +44,9 @@ _i32, _i64, _f32, _vp, _sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ct
 SIGNATURES = {
     'iqw_abi_version': (ctypes.c_int, []),
     'iqw_last_error': (ctypes.c_char_p, []),
+    'iqw_stft_workspace_bytes': (_sz, [_i32, _i64, _i64]),
     'iqw_stft_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i32, _f32,
-                                    _i32, _i32, _vp, _i64, _vp]),
+                                    _i32, _i32, _vp, _i64, _vp, _sz, _vp]),
     'iqw_time_stats_workspace_bytes': (_sz, [_i64, _i64, _i64, _i32]),
     'iqw_time_stats_f32': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, ctypes.POINTER(iqw_stat),
                                           _i32, _i32, _f32, _vp, _vp, _sz, _vp]),

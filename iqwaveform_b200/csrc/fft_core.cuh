@@ -209,7 +209,11 @@ IQW_HD void load_twiddles(float2* t, const float2* tw, int ltid) {
     }
 }
 
-template <int LOG2N, int P>
+// STRIDE == 0: one frame per exchange buffer, padded index (pad_index).  STRIDE > 0: STRIDE
+// independent transforms interleaved element by element (element i of transform c lives at
+// [i*STRIDE + c]; the caller passes src/dst already offset by c) -- used by the large-nfft
+// column pass, where the lanes of a warp run different transforms.
+template <int LOG2N, int P, int STRIDE = 0>
 IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* t, int ltid) {
     constexpr int N = 1 << LOG2N;
     constexpr int E = plan_elems(LOG2N);
@@ -227,7 +231,9 @@ IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* t,
         if constexpr (!FIRST) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if constexpr ((N / R) % 16 == 0)    // keep the r-offset a compile-time immediate
+                if constexpr (STRIDE > 0)
+                    a[r] = src[(j + r * (N / R)) * STRIDE];
+                else if constexpr ((N / R) % 16 == 0)    // keep the r-offset a compile-time immediate
                     a[r] = src[pad_index(j) + pad_index(r * (N / R))];
                 else
                     a[r] = src[pad_index(j + r * (N / R))];
@@ -240,7 +246,9 @@ IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* t,
             const int base = (j / Ns) * (Ns * R) + (j & (Ns - 1));
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if constexpr (Ns % 16 == 0)
+                if constexpr (STRIDE > 0)
+                    dst[(base + r * Ns) * STRIDE] = a[r];
+                else if constexpr (Ns % 16 == 0)
                     dst[pad_index(base) + pad_index(r * Ns)] = a[r];
                 else
                     dst[pad_index(base + r * Ns)] = a[r];

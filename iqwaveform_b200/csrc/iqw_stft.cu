@@ -17,25 +17,9 @@
 #include <mutex>
 #include <map>
 #include <utility>
-#include "iqw_common.cuh"
-#include "fft_core.cuh"
+#include "iqw_stft.cuh"
 
 namespace iqw {
-
-struct StftArgs {
-    const float2* x;
-    long long n_samples, x_ch_stride;
-    int n_channels;
-    const float* window;
-    const float2* twiddle;
-    long long hop, n_frames;
-    float eps;
-    int bin_lo, bin_hi;
-    void* out;
-    long long out_ch_stride;
-    long long n_groups;        // n_channels * groups_per_channel
-    long long groups_per_ch;   // ceil(n_frames / FPC)
-};
 
 template <int LOG2N>
 struct StftCfg {
@@ -185,7 +169,7 @@ __global__ void twiddle_init_kernel(float2* tw, int log2n) {
 static std::mutex g_tw_mutex;
 static std::map<std::pair<int, int>, float2*> g_tw_cache;
 
-static int get_twiddles(int log2n, cudaStream_t stream, const float2** out) {
+int get_twiddles(int log2n, cudaStream_t stream, const float2** out) {
     int dev = 0;
     IQW_CUDA_OK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_tw_mutex);
@@ -236,17 +220,25 @@ static int launch_stft_mode(const StftArgs& a, int mode, cudaStream_t s) {
 
 using namespace iqw;
 
+extern "C" size_t iqw_stft_workspace_bytes(int32_t nfft, int64_t n_channels, int64_t n_frames) {
+    if (nfft < 2 || (nfft & (nfft - 1))) return 0;
+    int log2n = 0;
+    while ((1 << log2n) < nfft) ++log2n;
+    return stft_large_workspace_bytes(log2n, n_channels, n_frames);
+}
+
 extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples,
                             int64_t x_channel_stride, const float* d_window, int32_t nfft,
                             int64_t hop, int64_t n_frames, int32_t mode, float eps, int32_t bin_lo,
-                            int32_t bin_hi, void* d_out, int64_t out_channel_stride, void* stream) {
+                            int32_t bin_hi, void* d_out, int64_t out_channel_stride, void* d_workspace,
+                            size_t workspace_bytes, void* stream) {
     if (!d_x || !d_window || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (nfft < 2 || (nfft & (nfft - 1)))
         return fail(IQW_ERR_UNSUPPORTED, "nfft=%d: only powers of two are built", nfft);
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
-    if (log2n < 4 || log2n > 13)
-        return fail(IQW_ERR_UNSUPPORTED, "nfft=%d outside the built range 16..8192", nfft);
+    if (log2n < 4 || log2n > 16)
+        return fail(IQW_ERR_UNSUPPORTED, "nfft=%d outside the built range 16..65536", nfft);
     if (hop < 1) return fail(IQW_ERR_INVALID, "hop=%lld must be >= 1", (long long)hop);
     if (n_channels < 0 || n_frames < 0) return fail(IQW_ERR_INVALID, "negative size");
     if (n_channels == 0 || n_frames == 0) return IQW_OK;
@@ -275,6 +267,7 @@ extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_sampl
     a.bin_hi = bin_hi;
     a.out = d_out;
     a.out_ch_stride = out_channel_stride;
+    if (log2n > 13) return launch_stft_large(a, log2n, mode, d_workspace, workspace_bytes, s);
     if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;
 
     switch (log2n) {

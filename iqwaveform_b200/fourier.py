@@ -127,10 +127,13 @@ def _stft_device(x2: torch.Tensor, *, window, nfft: int, noverlap: int, nzero: i
         raise ValueError(f'out must be a contiguous {dtype} tensor of shape {(C, T, nb)}')
     if T == 0 or C == 0:
         return out
+    ws_bytes = _lib.lib.iqw_stft_workspace_bytes(nfft, C, T)     # > 0 only for nfft > 8192
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device) if ws_bytes else None
     _lib.check(_lib.lib.iqw_stft_c64(
         ctypes.c_void_p(x2.data_ptr()), C, N, x2.stride(0) if C > 1 else N,
         ctypes.c_void_p(w.data_ptr()), nfft, hop, T, mode, eps, bin_lo, bin_hi,
-        ctypes.c_void_p(out.data_ptr()), T * nb, _stream_ptr(x2.device)))
+        ctypes.c_void_p(out.data_ptr()), T * nb, ctypes.c_void_p(ws.data_ptr()) if ws_bytes else None,
+        ws_bytes, _stream_ptr(x2.device)))
     return out
 
 

@@ -13,7 +13,7 @@ from oracle.make_golden import synth
 
 pytestmark = pytest.mark.gpu
 
-NFFTS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
+NFFTS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
 
 
 def dev_of(x, cuda_device):
@@ -98,6 +98,7 @@ def test_known_answers_on_gpu(cuda_device):
 @pytest.mark.parametrize('nfft,overlap,window', [(64, 0.75, 'hann'), (256, 0.5, 'hann'),
                                                  (1024, 0.5, 'hann'), (2048, 0.5, 'blackmanharris'),
                                                  (4096, 0.5, 'hann'), (8192, 0.75, ('kaiser', 10.0)),
+                                                 (16384, 0.5, 'hann'), (65536, 0.75, 'blackmanharris'),
                                                  (4096, 0.0, 'rect')])
 def test_spectrogram_vs_oracle_and_truth(cuda_device, nfft, overlap, window):
     nov = int(nfft * overlap)
@@ -158,7 +159,7 @@ def test_unsupported_sizes_fail_loudly(cuda_device):
     with pytest.raises(NotImplementedError):
         iqw.spectrogram(x, fs=1.0, window='hann', nperseg=1000)
     with pytest.raises(NotImplementedError):
-        iqw.spectrogram(x, fs=1.0, window='hann', nperseg=65536)
+        iqw.spectrogram(x, fs=1.0, window="hann", nperseg=131072)
     with pytest.raises(NotImplementedError):
         iqw.spectrogram(x.to(torch.complex128), fs=1.0, window='hann', nperseg=64)
 
