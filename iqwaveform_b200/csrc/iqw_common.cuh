@@ -61,10 +61,26 @@ __host__ __device__ __forceinline__ float key_to_float(uint32_t k) {
 #endif
 }
 
-// 10*log10(p + eps) in float32, same operation order as the reference's generic branch
-// (power_analysis.py:199-204: abs, += eps, log10, *= 10).
+// 10*log10(|p| + eps) in float32 (power_analysis.py:199-204: abs, += eps, log10, *= 10).
+// log10 is evaluated as (e + log2(m)) * log10(2) with v = m * 2^e, m in [1, 2): MUFU.LG2 on the
+// mantissa alone has an absolute error of ~4e-7, i.e. ~1.2e-6 dB, far inside the 5e-5 dB parity
+// bound, at a third of the instructions of log10f.  Zero, denormal, infinite and NaN arguments take
+// log10f so that -inf / nan come out exactly as the reference's.
+static __device__ __noinline__ float power_to_dB_slow(float v) { return 10.0f * log10f(v); }
+
 __device__ __forceinline__ float power_to_dB(float p, float eps) {
-    return 10.0f * log10f(fabsf(p) + eps);
+    const float v = fabsf(p) + eps;
+    const uint32_t b = __float_as_uint(v);
+    if (b - 0x00800000u < 0x7F000000u) {          // normal, finite, positive
+        // exponent as a float without I2F (which shares the quarter-rate XU pipe with MUFU):
+        // float(0x4B400000 | n) == 12582912 + n for n < 2^22
+        const float e = __uint_as_float(0x4B400000u | (b >> 23)) - 12583039.0f;
+        const float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(m));     // m in [1, 2): never denormal
+        return (e + l) * 3.01029995663981195f;
+    }
+    return power_to_dB_slow(v);                   // rare: out of line keeps the hot loops small
 }
 
 }  // namespace iqw
