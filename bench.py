@@ -90,7 +90,7 @@ def cpu_cores():
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
-        return 0
+        return None
     x = cpu_capture(CPU_SAMPLE)
     for _ in range(max(args.warmup, 1)):
         cpu_step(x)
@@ -113,8 +113,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,7 +281,7 @@ def run_b200(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return None
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     T = (n - NFFT) // (NFFT // 2) + 1
@@ -332,10 +331,26 @@ def run_b200(args):
         'config': workload_config(world, n), 'clocks': clocks, 'e2e': e2e,
         'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'impl': 'b200',
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line
+
+
+class QuietStdout:
+    """everything libraries print to fd 1 while the benchmark runs (NCCL's version banner, ...)
+    goes to stderr, so that stdout carries exactly one JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -350,7 +365,11 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
-        return run_reference(args)
+        with QuietStdout():
+            line = run_reference(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return 0
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
@@ -358,7 +377,11 @@ def main():
                f'--nproc-per-node={args.gpus}', '--master-addr', '127.0.0.1', '--master-port', '29517',
                os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_b200(args)
+    with QuietStdout():
+        line = run_b200(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == '__main__':
