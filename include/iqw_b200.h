@@ -133,6 +133,10 @@ int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_channel_str
 int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_channel_stride,
                                 int64_t bin_len, int64_t n_bins, float* d_out, void* stream);
 
+/* Tuning aid: bytes of scratch iqw_stft_workspace_bytes asks for (nfft > 8192); frames are
+ * processed in chunks of that size. */
+int iqw_debug_set_stft_scratch_cap(size_t bytes);
+
 /* Test aid: width of the brackets the row sample puts around each target rank on the long-column
  * path of iqw_time_stats_f32 (default 6 sigma + 2 ranks).  Results are exact for ANY setting -- a
  * bracket that misses its rank is refined like any other interval -- which is what the tests use

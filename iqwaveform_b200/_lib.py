@@ -53,6 +53,7 @@ SIGNATURES = {
     'iqw_bin_power_workspace_bytes': (_sz, [_i64, _i64, _i64]),
     'iqw_bin_power_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     'iqw_envtopow_transposed_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    'iqw_debug_set_stft_scratch_cap': (ctypes.c_int, [_sz]),
     'iqw_debug_set_sample_margin': (ctypes.c_int, [ctypes.c_double, ctypes.c_int]),
     'iqw_debug_time_stats_counters': (ctypes.c_int, [_vp, _i64, ctypes.POINTER(ctypes.c_uint32)]),
     'iqw_profile_enable': (ctypes.c_int, [ctypes.c_int]),

@@ -16,7 +16,7 @@
 //                    |X|^2 / dB / band trim.  Output bin k = k1 + N1*k2 is strided, so the 16 rows of
 //                    a CTA go through a shared-memory tile and leave as 64/128-byte segments.
 // The scratch is written and read once (16*nfft/hop bytes per sample of extra HBM traffic); frames
-// are processed in chunks so that it never exceeds kScratchCap.
+// are processed in chunks so that it never exceeds the scratch cap.
 #include <algorithm>
 #include <mutex>
 #include <map>
@@ -27,7 +27,7 @@ namespace iqw {
 constexpr int kLog2N2 = 8;
 constexpr int kN2 = 1 << kLog2N2;
 constexpr int kCols = 16;                         // n2 per CTA of columns_kernel / k1 per CTA of rows_kernel
-constexpr size_t kScratchCap = 1ull << 30;        // bytes of scratch per chunk of frames
+static size_t g_scratch_cap = 1ull << 30;         // bytes of scratch per chunk of frames (iqw_debug_set_stft_scratch_cap)
 
 struct LargeArgs {
     StftArgs a;
@@ -278,7 +278,7 @@ size_t stft_large_workspace_bytes(int log2n, long long n_channels, long long n_f
     if (log2n < 14 || log2n > 16 || n_channels < 1 || n_frames < 1) return 0;
     const size_t frame_bytes = sizeof(float2) << log2n;
     const size_t all = frame_bytes * (size_t)n_channels * (size_t)n_frames;
-    const size_t cap = kScratchCap / frame_bytes * frame_bytes;
+    const size_t cap = g_scratch_cap / frame_bytes * frame_bytes > 0 ? g_scratch_cap / frame_bytes * frame_bytes : frame_bytes;
     return all < cap ? all : cap;
 }
 
@@ -361,3 +361,8 @@ int launch_stft_large(const StftArgs& a, int log2n, int mode, void* workspace, s
 }
 
 }  // namespace iqw
+
+extern "C" int iqw_debug_set_stft_scratch_cap(size_t bytes) {
+    iqw::g_scratch_cap = bytes;
+    return IQW_OK;
+}
