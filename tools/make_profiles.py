@@ -23,6 +23,9 @@ if os.path.exists(launches):
     rows = list(csv.DictReader(io.StringIO(text[start:])))
     per = collections.OrderedDict()
     ours = [r for r in rows if r.get('Metric Name') == 'gpu__time_duration.sum']
+    # keep the last complete step: from the last stft_kernel launch on
+    last = max((i for i, r in enumerate(ours) if 'stft_kernel' in r['Kernel Name']), default=0)
+    ours = ours[last:]
     with open(os.path.join(out, f'launches_{tag}.csv'), 'w') as f:
         f.write('id,kernel,grid,block,duration_us\n')
         for r in ours:
