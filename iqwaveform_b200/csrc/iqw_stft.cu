@@ -60,7 +60,8 @@ struct PassLoop {
     }
 };
 
-template <int LOG2N, int MODE>
+// FULLBAND: every bin is stored (bin_lo == 0, bin_hi == nfft), so the per-bin range checks vanish
+template <int LOG2N, int MODE, bool FULLBAND>
 __global__ void __launch_bounds__(StftCfg<LOG2N>::THREADS, StftCfg<LOG2N>::MIN_BLOCKS)
 stft_kernel(const StftArgs a) {
     using C = StftCfg<LOG2N>;
@@ -93,14 +94,17 @@ stft_kernel(const StftArgs a) {
     const int nbins = a.bin_hi - a.bin_lo;
     int par = 0;
 
+    // (channel, frame group) of g_begin, then advanced incrementally: no 64-bit divisions in the loop
+    long long c_nx = g_begin / a.groups_per_ch;
+    long long gc_nx = g_begin - c_nx * a.groups_per_ch;
+
     // software pipeline: the samples of the NEXT frame group are loaded into registers while the
     // current one is transformed (they are only multiplied by the window when their turn comes)
     float2 nx[E];
     auto prefetch = [&](long long g) {
-        const long long c = g / a.groups_per_ch;
-        const long long frame = (g - c * a.groups_per_ch) * FPC + slot;
+        const long long frame = gc_nx * FPC + slot;
         if (g < g_end && frame < a.n_frames) {
-            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
+            const float2* src = a.x + c_nx * a.x_ch_stride + frame * a.hop + ltid;
 #pragma unroll
             for (int q = 0; q < E / R0; ++q)
 #pragma unroll
@@ -113,9 +117,10 @@ stft_kernel(const StftArgs a) {
     prefetch(g_begin);
 
     for (long long g = g_begin; g < g_end; ++g) {
-        const long long c = g / a.groups_per_ch;
-        const long long frame = (g - c * a.groups_per_ch) * FPC + slot;
+        const long long c = c_nx;
+        const long long frame = gc_nx * FPC + slot;
         const bool valid = frame < a.n_frames;
+        if (++gc_nx == a.groups_per_ch) { gc_nx = 0; ++c_nx; }
 
         float2 v[E];
 #pragma unroll
@@ -131,7 +136,7 @@ stft_kernel(const StftArgs a) {
 #pragma unroll
                 for (int r = 0; r < RL; ++r) {
                     const int k = (ltid + q * TPF) + r * (N / RL);
-                    if (k >= a.bin_lo && k < a.bin_hi) {
+                    if (FULLBAND || (k >= a.bin_lo && k < a.bin_hi)) {
                         const float2 X = v[q * RL + r];
                         if constexpr (MODE == IQW_STFT_COMPLEX) {
                             __stcs(reinterpret_cast<float2*>(a.out) + row + k, X);
@@ -188,10 +193,10 @@ int get_twiddles(int log2n, cudaStream_t stream, const float2** out) {
     return IQW_OK;
 }
 
-template <int LOG2N, int MODE>
-static int launch_stft(StftArgs a, cudaStream_t stream) {
+template <int LOG2N, int MODE, bool FULLBAND>
+static int launch_stft_band(StftArgs a, cudaStream_t stream) {
     using C = StftCfg<LOG2N>;
-    auto kern = stft_kernel<LOG2N, MODE>;
+    auto kern = stft_kernel<LOG2N, MODE, FULLBAND>;
     IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     int sms = 0, per_sm = 0;
     if (int rc = device_sm_count(&sms)) return rc;
@@ -204,6 +209,12 @@ static int launch_stft(StftArgs a, cudaStream_t stream) {
     { IQW_PROFILE("stft_kernel", stream); kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(a); }
     IQW_CUDA_OK(cudaGetLastError());
     return IQW_OK;
+}
+
+template <int LOG2N, int MODE>
+static int launch_stft(const StftArgs& a, cudaStream_t stream) {
+    if (a.bin_lo == 0 && a.bin_hi == (1 << LOG2N)) return launch_stft_band<LOG2N, MODE, true>(a, stream);
+    return launch_stft_band<LOG2N, MODE, false>(a, stream);
 }
 
 template <int LOG2N>
