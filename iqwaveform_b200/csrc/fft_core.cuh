@@ -85,8 +85,25 @@ IQW_HD constexpr int padded_size(int n) { return n + (n >> 4); }
 // ------------------------------------------------------------------------------------------
 // complex helpers
 // ------------------------------------------------------------------------------------------
+// complex add / subtract: on the device one packed f32x2 instruction (sm_100a FADD2 / FFMA2) on the
+// (re, im) register pair -- same IEEE results as the scalar pair, half the issue slots
+#if defined(__CUDA_ARCH__) && defined(IQW_PACKED_F32X2)
+IQW_HD float2 cadd(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 p, q; mov.b64 p, {%2, %3}; mov.b64 q, {%4, %5}; add.rn.f32x2 p, p, q; mov.b64 {%0, %1}, p; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+IQW_HD float2 csub(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 p, q; mov.b64 p, {%2, %3}; mov.b64 q, {%4, %5}; sub.rn.f32x2 p, p, q; mov.b64 {%0, %1}, p; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+#else
 IQW_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 IQW_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 IQW_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
