@@ -1102,13 +1102,6 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
 
     const uint32_t cap_sum = bp.cap_sum;
     const bool raw = w.pending[8] == 0;     // lists hold raw float bits (bracket pass RAW mode)
-    // bracket of a key among those in `mode` (brackets are disjoint), -1 if none
-    auto bracket_of = [&](uint32_t k, uint32_t mode) {
-        int g = -1;
-#pragma unroll
-        for (int q = 0; q < M; ++q) g = (s_mode[q] == mode && k >= s_a[q] && k <= s_b[q]) ? q : g;
-        return g;
-    };
     auto sweep = [&](auto&& visit) {
         const long long stride = cols * (long long)cap_sum;
         const uint32_t* base = w.lists + (long long)col * cap_sum;
@@ -1133,10 +1126,23 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
         // ---- histogram sweep over the brackets in SEL_HIST ----
         for (int i = t; i < M * kSelBins; i += kSelThreads) hist[i] = 0;
         __syncthreads();
-        sweep([&](uint32_t k) {
-            const int g = bracket_of(k, SEL_HIST);
-            if (g >= 0) atomicAdd(&hist[g * kSelBins + ((k - s_a[g]) >> s_sh[g])], 1u);
-        });
+        {   // bracket parameters in registers for the sweep (a bracket not in SEL_HIST gets an empty range)
+            uint32_t ra[M], rw[M], rsh[M];
+#pragma unroll
+            for (int g = 0; g < M; ++g) {
+                const bool on = s_mode[g] == SEL_HIST;
+                ra[g] = on ? s_a[g] : 0xFFFFFFFFu;
+                rw[g] = on ? s_b[g] - s_a[g] : 0u;          // k in [a, b]  <=>  k - a <= b - a (unsigned)
+                rsh[g] = s_sh[g];
+            }
+            sweep([&](uint32_t k) {
+#pragma unroll
+                for (int g = 0; g < M; ++g) {
+                    const uint32_t d = k - ra[g];
+                    if (d <= rw[g] && ra[g] != 0xFFFFFFFFu) atomicAdd(&hist[g * kSelBins + (d >> rsh[g])], 1u);
+                }
+            });
+        }
         __syncthreads();
 
         // ---- a warp per bracket: where are its ranks? ----
@@ -1237,15 +1243,28 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     if (!any_collect) return;
 
     // ---- second sweep: the keys of the target bins ----
-    sweep([&](uint32_t k) {
-        const int g = bracket_of(k, SEL_COLLECT);
-        if (g < 0) return;
-        const uint32_t b = (k - s_a[g]) >> s_sh[g];
-        if (b >= s_bf[g] && b <= s_bl[g]) {
-            const uint32_t pos = atomicAdd(&s_n[g], 1u);
-            if (pos < (uint32_t)kSelBuf) buf[g * kSelBuf + pos] = k;
+    {   // key range of the target bins of every collecting bracket, in registers
+        uint32_t ra[M], rw[M];
+#pragma unroll
+        for (int g = 0; g < M; ++g) {
+            const bool on = s_mode[g] == SEL_COLLECT;
+            const uint32_t sh = s_sh[g];
+            const uint32_t lo = s_a[g] + (s_bf[g] << sh);
+            unsigned long long hi = (unsigned long long)s_a[g] + (((unsigned long long)s_bl[g] + 1ull) << sh) - 1ull;
+            if (hi > (unsigned long long)s_b[g]) hi = s_b[g];
+            ra[g] = on ? lo : 0xFFFFFFFFu;
+            rw[g] = on ? (uint32_t)hi - lo : 0u;
         }
-    });
+        sweep([&](uint32_t k) {
+#pragma unroll
+            for (int g = 0; g < M; ++g) {
+                if (k - ra[g] <= rw[g] && ra[g] != 0xFFFFFFFFu) {
+                    const uint32_t pos = atomicAdd(&s_n[g], 1u);
+                    if (pos < (uint32_t)kSelBuf) buf[g * kSelBuf + pos] = k;
+                }
+            }
+        });
+    }
     __syncthreads();
 
     // ---- rank by counting: key e answers position q iff less(e) <= q < less(e) + equal(e) ----
