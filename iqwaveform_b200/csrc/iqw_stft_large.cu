@@ -104,23 +104,36 @@ columns_kernel(const LargeArgs g) {
     const long long it1 = it0 + per < n_items ? it0 + per : n_items;
     int par = 0;
 
+    // software pipeline: samples and window of the next item are loaded while this one is transformed
+    float2 nx[E];
+    float nw[E];
+    auto prefetch = [&](long long it) {
+        if (it < it1) {
+            const long long gf = g.gf0 + it / TILES;
+            const int n2 = (int)(it % TILES) * kCols + col;
+            const long long c = gf / a.n_frames, frame = gf - c * a.n_frames;
+            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + n2;
+            const float* win = a.window + n2;
+#pragma unroll
+            for (int q = 0; q < E / R0; ++q)
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+                    const int n1 = (ltid + q * TPF) + r * (N1 / R0);
+                    nx[q * R0 + r] = __ldg(src + (long long)n1 * kN2);
+                    nw[q * R0 + r] = __ldg(win + n1 * kN2);
+                }
+        }
+    };
+    prefetch(it0);
+
     for (long long it = it0; it < it1; ++it) {
         const long long gf = g.gf0 + it / TILES;
         const int n2 = (int)(it % TILES) * kCols + col;
-        const long long c = gf / a.n_frames, frame = gf - c * a.n_frames;
-        const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + n2;
-        const float* win = a.window + n2;
 
         float2 v[E];
 #pragma unroll
-        for (int q = 0; q < E / R0; ++q)
-#pragma unroll
-            for (int r = 0; r < R0; ++r) {
-                const int n1 = (ltid + q * TPF) + r * (N1 / R0);
-                const float2 s = __ldg(src + (long long)n1 * kN2);
-                const float w = __ldg(win + n1 * kN2);
-                v[q * R0 + r] = make_float2(s.x * w, s.y * w);
-            }
+        for (int e = 0; e < E; ++e) v[e] = make_float2(nx[e].x * nw[e], nx[e].y * nw[e]);
+        prefetch(it + 1);
         ColPasses<L1, 0>::run(v, bufs, tw, nullptr, ltid, col, par);
 
         float2* dst = g.scratch + (gf - g.gf0) * N + n2;
@@ -185,7 +198,8 @@ rows_kernel(const LargeArgs g, int log2n1) {
 
     const int slot = threadIdx.x / kRowTPF;             // row (k1) within the tile
     const int ltid = threadIdx.x % kRowTPF;
-    const int tiles = N1 / kCols;
+    const int tiles = N1 / kCols;                       // power of two
+    const int tile_shift = log2n1 - 4;
     const long long n_items = (g.gf1 - g.gf0) * tiles;
     const long long per = (n_items + gridDim.x - 1) / gridDim.x;
     const long long it0 = per * blockIdx.x;
@@ -193,15 +207,28 @@ rows_kernel(const LargeArgs g, int log2n1) {
     const int nbins = a.bin_hi - a.bin_lo;
     int par = 0;
 
+    // software pipeline: the rows of the next item are loaded while this one is transformed
+    float2 nx[kRowE];
+    auto prefetch = [&](long long it) {
+        if (it < it1) {
+            const long long gf = g.gf0 + (it >> tile_shift);
+            const int k1_0 = (int)(it & (tiles - 1)) * kCols;
+            const float2* src = g.scratch + (gf - g.gf0) * N + (long long)(k1_0 + slot) * kN2 + ltid;
+#pragma unroll
+            for (int r = 0; r < R0; ++r) nx[r] = __ldcs(src + r * (kN2 / R0));
+        }
+    };
+    prefetch(it0);
+
     for (long long it = it0; it < it1; ++it) {
-        const long long gf = g.gf0 + it / tiles;
-        const int k1_0 = (int)(it % tiles) * kCols;
+        const long long gf = g.gf0 + (it >> tile_shift);
+        const int k1_0 = (int)(it & (tiles - 1)) * kCols;
         const long long c = gf / a.n_frames, frame = gf - c * a.n_frames;
-        const float2* src = g.scratch + (gf - g.gf0) * N + (long long)(k1_0 + slot) * kN2 + ltid;
 
         float2 v[kRowE];
 #pragma unroll
-        for (int r = 0; r < R0; ++r) v[r] = __ldcs(src + r * (kN2 / R0));
+        for (int r = 0; r < R0; ++r) v[r] = nx[r];
+        prefetch(it + 1);
         RowPasses<0>::run(v, bufs, tw, nullptr, ltid, slot, par);
 
         // tile[k2][slot] <- result of bin k2 = ltid + r*16; then rows of 16 adjacent k leave together
