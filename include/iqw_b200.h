@@ -138,7 +138,7 @@ int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_c
 int iqw_debug_set_stft_scratch_cap(size_t bytes);
 
 /* Test aid: width of the brackets the row sample puts around each target rank on the long-column
- * path of iqw_time_stats_f32 (default 6 sigma + 2 ranks).  Results are exact for ANY setting -- a
+ * path of iqw_time_stats_f32 (default 5 sigma + 2 ranks).  Results are exact for ANY setting -- a
  * bracket that misses its rank is refined like any other interval -- which is what the tests use
  * this for (margin 0 makes about half of the brackets miss). */
 int iqw_debug_set_sample_margin(double sigmas, int extra_ranks);

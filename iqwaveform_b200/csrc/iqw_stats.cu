@@ -29,7 +29,7 @@
 //   A. sample_brackets : a stratified, jittered ROW SAMPLE (<= 8192 rows) of two columns per CTA is
 //      staged in shared memory; a two-level histogram (2048 bins, then 256 sub-bins around each
 //      wanted sample rank) gives, per group of target ranks, a key BRACKET [lo, hi] that holds the
-//      group's ranks unless the sample was > 6 sigma off
+//      group's ranks unless the sample was > 5 sigma off (a miss costs time, never exactness)
 //   B. bracket_pass    : the single pass over ALL rows.  A thread owns a column and keeps the
 //      brackets in registers; per bracket it counts the keys below it and appends the keys inside
 //      it to a private candidate list (~15 % of the elements in total), + exact min / max / sum
@@ -1379,7 +1379,7 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
 
 // long-column plan: row splits of the bracket pass, the row sample, and per group of target
 // ranks the two SAMPLE ranks (margin-sigma away) whose keys bracket it.
-static double g_margin_sigmas = 6.0;   // test aid: iqw_debug_set_sample_margin
+static double g_margin_sigmas = 5.0;   // iqw_debug_set_sample_margin; 5 sigma: ~1 % of config-3 calls refine one column
 static int g_margin_extra = 2;
 
 struct LongPlan {

@@ -11,7 +11,10 @@ x = bench.device_capture(torch, n, 1234, dev).view(1, n)
 _, _, p = iqw.spectrogram(x, fs=100e6, window='hann', nperseg=4096, noverlap=2048, axis=1)
 print('spectrogram', tuple(p.shape))
 ALL = ([0.1, 0.5, 0.9, 0.999], [0.5], [0.5, 0.99, 'mean', 'max'])
-sel = [ALL[int(a)] for a in sys.argv[2:]] or ALL
+sel = [ALL[int(a)] for a in sys.argv[2:] if not a.startswith('m=')] or ALL
+for a in sys.argv[2:]:
+    if a.startswith('m='):
+        _lib.lib.iqw_debug_set_sample_margin(float(a[2:]), 2)
 for stats in sel:
     cnt = []
     out = iqw.time_statistics(p, stats, dB=True, counters=cnt)
