@@ -124,7 +124,7 @@ stft_kernel(const StftArgs a) {
 
         float2 v[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = make_float2(nx[e].x * w[e], nx[e].y * w[e]);
+        for (int e = 0; e < E; ++e) v[e] = cscale(nx[e], w[e]);
         prefetch(g + 1);
 
         PassLoop<LOG2N, 0>::run(v, bufs, tw, nullptr, ltid, slot, par);

@@ -38,9 +38,7 @@ struct LargeArgs {
     int mode;
 };
 
-__device__ __forceinline__ float2 cmul_d(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
+__device__ __forceinline__ float2 cmul_d(float2 a, float2 b) { return cmul(a, b); }
 
 // ---------------------------------------------------------------------------------------------
 // columns
@@ -132,7 +130,7 @@ columns_kernel(const LargeArgs g) {
 
         float2 v[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = make_float2(nx[e].x * nw[e], nx[e].y * nw[e]);
+        for (int e = 0; e < E; ++e) v[e] = cscale(nx[e], nw[e]);
         prefetch(it + 1);
         ColPasses<L1, 0>::run(v, bufs, tw, nullptr, ltid, col, par);
 
