@@ -109,11 +109,10 @@ stft_kernel(const StftArgs a) {
             for (int q = 0; q < E / R0; ++q)
 #pragma unroll
                 for (int r = 0; r < R0; ++r) nx[q * R0 + r] = __ldg(src + q * TPF + r * (N / R0));
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) nx[e] = make_float2(0.f, 0.f);
-        }
+        }       // (a slot past the last frame keeps stale values: its results are never stored)
     };
+#pragma unroll
+    for (int e = 0; e < E; ++e) nx[e] = make_float2(0.f, 0.f);
     prefetch(g_begin);
 
     for (long long g = g_begin; g < g_end; ++g) {
