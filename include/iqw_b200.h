@@ -133,6 +133,19 @@ int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_channel_str
 int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels, int64_t x_channel_stride,
                                 int64_t bin_len, int64_t n_bins, float* d_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise power transforms (power_analysis.py:168-298): float32 out, one streaming pass.
+ *   op 0 powtodB  : 10*log10(abs(x) + eps)   (use_abs == 0: 10*log10(x + eps))
+ *   op 1 dBtopow  : 10**(x/10)
+ *   op 2 envtopow : abs(x)**2
+ *   op 3 envtodB  : 20*log10(abs(x) + eps)   (use_abs == 0: 20*log10(x + eps))
+ * iqw_elementwise_c64 takes complex64 input and supports ops 2 and 3 (abs is the modulus).
+ */
+typedef enum iqw_ew_op { IQW_EW_POWTODB = 0, IQW_EW_DBTOPOW = 1, IQW_EW_ENVTOPOW = 2, IQW_EW_ENVTODB = 3 } iqw_ew_op;
+int iqw_elementwise_f32(int32_t op, const float* d_in, float* d_out, int64_t n, int32_t use_abs, float eps,
+                        void* stream);
+int iqw_elementwise_c64(int32_t op, const void* d_in, float* d_out, int64_t n, float eps, void* stream);
+
 /* Tuning aid: bytes of scratch iqw_stft_workspace_bytes asks for (nfft > 8192); frames are
  * processed in chunks of that size. */
 int iqw_debug_set_stft_scratch_cap(size_t bytes);

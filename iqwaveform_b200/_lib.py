@@ -24,6 +24,7 @@ IQW_ERR_WORKSPACE = -4
 
 STFT_COMPLEX, STFT_POWER, STFT_DB = 0, 1, 2
 STAT_QUANTILE, STAT_MEAN, STAT_MAX, STAT_MIN, STAT_MEDIAN = 0, 1, 2, 3, 4
+EW_POWTODB, EW_DBTOPOW, EW_ENVTOPOW, EW_ENVTODB = 0, 1, 2, 3
 
 MAX_RANKS_PER_CALL = 8
 
@@ -53,6 +54,8 @@ SIGNATURES = {
     'iqw_bin_power_workspace_bytes': (_sz, [_i64, _i64, _i64]),
     'iqw_bin_power_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     'iqw_envtopow_transposed_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    'iqw_elementwise_f32': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i32, _f32, _vp]),
+    'iqw_elementwise_c64': (ctypes.c_int, [_i32, _vp, _vp, _i64, _f32, _vp]),
     'iqw_debug_set_stft_scratch_cap': (ctypes.c_int, [_sz]),
     'iqw_debug_set_sample_margin': (ctypes.c_int, [ctypes.c_double, ctypes.c_int]),
     'iqw_debug_time_stats_counters': (ctypes.c_int, [_vp, _i64, ctypes.POINTER(ctypes.c_uint32)]),

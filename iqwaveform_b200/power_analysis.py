@@ -1,8 +1,11 @@
 """B200-native ``iq_to_bin_power`` with the reference signature
-(/root/reference/src/iqwaveform/power_analysis.py:341-385)."""
+(/root/reference/src/iqwaveform/power_analysis.py:341-385) and the elementwise power transforms
+``powtodB`` / ``dBtopow`` / ``envtopow`` / ``envtodB`` / ``dBlinmean`` / ``dBlinsum``
+(power_analysis.py:168-338), each one streaming CUDA kernel behind ``iqw_elementwise_*``."""
 from __future__ import annotations
 
 import ctypes
+import math
 from numbers import Number
 
 import torch
@@ -10,7 +13,7 @@ import torch
 from . import _arrays, _lib, _plan
 from .fourier import _stream_ptr, time_statistics
 
-__all__ = ['iq_to_bin_power']
+__all__ = ['iq_to_bin_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean', 'dBlinsum']
 
 _DIRECT = {'mean': 'mean', 'rms': 'mean', 'max': 'max', 'peak': 'max', 'min': 'min'}
 
@@ -80,3 +83,101 @@ def iq_to_bin_power(iq, Ts: float, Tbin: float, randomize: bool = False, kind='m
             ctypes.c_void_p(pt.data_ptr()), _stream_ptr(dev)))
         time_statistics(pt, [kind], dB=False, out=out.view(C, 1, n_bins))
     return res.give_back(_arrays.restore_layout(out, lead, trail, 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# elementwise transforms (power_analysis.py:168-338)
+# ---------------------------------------------------------------------------------------------
+def _elementwise(x, op: int, *, use_abs: bool = True, eps: float = 0.0, out=None):
+    """float32 / complex64 array-like -> float32 of the same shape, in the caller's kind"""
+    if isinstance(x, Number):            # scalars never touch the device (reference: numexpr)
+        if op == _lib.EW_DBTOPOW:
+            return 10.0 ** (x / 10.0)
+        if op == _lib.EW_ENVTOPOW:
+            return float(abs(x)) ** 2
+        v = (abs(x) if use_abs else x) + eps
+        scale = 10.0 if op == _lib.EW_POWTODB else 20.0
+        if v == 0:
+            return -math.inf
+        return scale * math.log10(v) if v > 0 else math.nan
+    xd, res = _arrays.to_device(x)
+    if xd.dtype == torch.complex64:
+        if op not in (_lib.EW_ENVTOPOW, _lib.EW_ENVTODB):
+            raise TypeError('powtodB / dBtopow expect real input')
+        if not use_abs:
+            raise NotImplementedError('abs=False on complex input is not built')
+    elif xd.dtype != torch.float32:
+        raise NotImplementedError(f'only float32 and complex64 input is built (got {xd.dtype})')
+    xc = xd.contiguous()
+    if out is not None:
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float32 and
+                out.shape == xc.shape and out.is_contiguous()):
+            raise ValueError('out must be a contiguous float32 CUDA tensor of the input shape')
+        y = out
+    else:
+        y = torch.empty(xc.shape, dtype=torch.float32, device=xc.device)
+    n = xc.numel()
+    if xc.dtype == torch.complex64:
+        _lib.check(_lib.lib.iqw_elementwise_c64(op, ctypes.c_void_p(xc.data_ptr()), ctypes.c_void_p(y.data_ptr()),
+                                                n, float(eps), _stream_ptr(xc.device)))
+    else:
+        _lib.check(_lib.lib.iqw_elementwise_f32(op, ctypes.c_void_p(xc.data_ptr()), ctypes.c_void_p(y.data_ptr()),
+                                                n, int(bool(use_abs)), float(eps), _stream_ptr(xc.device)))
+    return y if out is not None else res.give_back(y)
+
+
+def powtodB(x, abs: bool = True, eps: float = 0, out=None):
+    """``10*log10(abs(x) + eps)`` (or without abs), power_analysis.py:168-206"""
+    return _elementwise(x, _lib.EW_POWTODB, use_abs=abs, eps=eps, out=out)
+
+
+def dBtopow(x, out=None):
+    """``10**(x/10)``, power_analysis.py:209-231"""
+    return _elementwise(x, _lib.EW_DBTOPOW, out=out)
+
+
+def envtopow(x, out=None):
+    """``abs(x)**2`` of a real or complex waveform, power_analysis.py:234-257"""
+    return _elementwise(x, _lib.EW_ENVTOPOW, out=out)
+
+
+def envtodB(x, abs: bool = True, eps: float = 0, out=None):
+    """``20*log10(abs(x) + eps)`` (or without abs), power_analysis.py:260-298"""
+    return _elementwise(x, _lib.EW_ENVTODB, use_abs=abs, eps=eps, out=out)
+
+
+def _dBlin(x_dB, axis, reduce: str):
+    """powtodB(dBtopow(x).<mean|sum>(axis)) (power_analysis.py:301-338).  dBtopow and powtodB run in
+    the elementwise kernel, the reduction of the linear power in the time-statistics kernel, whose
+    reduction axis is the row axis of a (channels, rows, columns) layout: built for axis 0 of a
+    2-D array, axis 1 (-2) of a 3-D array, and for 1-D arrays / axis=None up to 2**20 elements."""
+    xd, res = _arrays.to_device(x_dB)
+    lin = _elementwise(xd, _lib.EW_DBTOPOW)
+    nd = lin.ndim
+    ax = None if axis is None else (axis + nd if axis < 0 else axis)
+    if ax is None or nd == 1:
+        if lin.numel() > (1 << 20):
+            raise NotImplementedError('reduce large arrays along axis 0 of a 2-D (rows, columns) layout')
+        lin3, out_shape = lin.reshape(1, -1, 1), ()
+    elif nd == 2 and ax == 0:
+        lin3, out_shape = lin.reshape(1, lin.shape[0], lin.shape[1]), (lin.shape[1],)
+    elif nd == 3 and ax == 1:
+        lin3, out_shape = lin, (lin.shape[0], lin.shape[2])
+    else:
+        raise NotImplementedError('dBlinmean / dBlinsum are built for axis 0 of 2-D and axis 1 of 3-D arrays')
+    n = lin3.shape[1]
+    mean = time_statistics(lin3, ['mean'], dB=False)              # (C, 1, cols) float32
+    y = _elementwise(mean, _lib.EW_POWTODB)                          # 10*log10(mean)
+    if reduce == 'sum':                                               # log10(n * mean) = log10(mean) + log10(n)
+        y.add_(10.0 * math.log10(n))     # (C, cols) scalars-per-column epilogue on the reduced result
+    return res.give_back(y.reshape(out_shape))
+
+
+def dBlinmean(x_dB, axis=None, overwrite_x=False):
+    """mean in linear power of values in dB, power_analysis.py:301-318"""
+    return _dBlin(x_dB, axis, 'mean')
+
+
+def dBlinsum(x_dB, axis=None, overwrite_x=False):
+    """sum in linear power of values in dB, power_analysis.py:321-338"""
+    return _dBlin(x_dB, axis, 'sum')

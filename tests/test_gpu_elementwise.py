@@ -1,0 +1,84 @@
+"""GPU parity of the elementwise power transforms (power_analysis.py:168-338) against the numpy
+oracle (the reference's generic branch) on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import iqwaveform_b200 as iqw
+from oracle import iqw_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x, d):
+    return torch.from_numpy(x).to(d)
+
+
+@pytest.mark.parametrize('n', [1, 3, 1000, 4097, 1 << 20])
+def test_powtodB_dBtopow_envtopow_envtodB(cuda_device, n):
+    rng = np.random.default_rng(n)
+    p = rng.exponential(1e-6, n).astype(np.float32)
+    p[::7] = 0.0                                   # log of zero -> -inf, as in the reference
+    got = iqw.powtodB(_dev(p, cuda_device)).cpu().numpy()
+    want = orc.powtodB(p.copy())
+    assert np.array_equal(np.isneginf(got), np.isneginf(want))
+    f = np.isfinite(want)
+    assert np.max(np.abs(got[f] - want[f]), initial=0) <= 5e-5          # dB
+    got = iqw.powtodB(_dev(p, cuda_device), eps=1e-25).cpu().numpy()
+    assert np.max(np.abs(got - orc.powtodB(p.copy(), eps=1e-25))) <= 5e-5
+    # abs=False: negative arguments are NaN
+    s = (p - 5e-7).astype(np.float32)
+    got = iqw.powtodB(_dev(s, cuda_device), abs=False).cpu().numpy()
+    want = orc.powtodB_noabs(s)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    f = np.isfinite(want)
+    assert np.max(np.abs(got[f] - want[f]), initial=0) <= 5e-5
+
+    d = rng.uniform(-150, 30, n).astype(np.float32)
+    got = iqw.dBtopow(_dev(d, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(got, orc.dBtopow(d), rtol=3e-6)
+
+    z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    got = iqw.envtopow(_dev(z, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(got, orc.envtopow(z), rtol=4e-7)         # re^2+im^2 vs hypot^2
+    got = iqw.envtopow(_dev(d, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(got, orc.envtopow(d), rtol=1e-7)
+    got = iqw.envtodB(_dev(z, cuda_device)).cpu().numpy()
+    assert np.max(np.abs(got - orc.envtodB(z))) <= 5e-5
+    got = iqw.envtodB(_dev(z, cuda_device), eps=1e-3).cpu().numpy()
+    assert np.max(np.abs(got - orc.envtodB(z, eps=1e-3))) <= 5e-5
+    got = iqw.envtodB(_dev(np.abs(d) + 1, cuda_device), abs=False).cpu().numpy()
+    assert np.max(np.abs(got - orc.envtodB(np.abs(d) + 1, abs=False))) <= 5e-5
+
+
+def test_elementwise_kinds_and_scalars(cuda_device):
+    p = np.array([1.0, 10.0, 100.0], np.float32)
+    out = iqw.powtodB(p)                                   # numpy in -> numpy out
+    assert isinstance(out, np.ndarray) and np.allclose(out, [0, 10, 20], atol=5e-5)
+    assert iqw.powtodB(1) == 0 and iqw.powtodB(100.0) == 20.0          # reference tests/test_transforms.py
+    assert iqw.dBtopow(20.0) == pytest.approx(100.0)
+    assert iqw.envtodB(10.0) == pytest.approx(20.0)
+    with pytest.raises(NotImplementedError):
+        iqw.powtodB(torch.zeros(4, dtype=torch.float64, device=cuda_device))
+    with pytest.raises(TypeError):
+        iqw.powtodB(torch.zeros(4, dtype=torch.complex64, device=cuda_device))
+    buf = torch.empty(3, dtype=torch.float32, device=cuda_device)
+    r = iqw.envtopow(_dev(p, cuda_device), out=buf)
+    assert r is buf and np.allclose(buf.cpu().numpy(), p * p)
+
+
+def test_dBlinmean_dBlinsum(cuda_device):
+    rng = np.random.default_rng(3)
+    d = rng.uniform(-120, -60, (5000, 96)).astype(np.float32)
+    lin = 10.0 ** (d.astype(np.float64) / 10)
+    got = iqw.dBlinmean(_dev(d, cuda_device), axis=0).cpu().numpy()
+    np.testing.assert_allclose(got, 10 * np.log10(lin.mean(axis=0)), atol=1e-4)
+    got = iqw.dBlinsum(_dev(d, cuda_device), axis=0).cpu().numpy()
+    np.testing.assert_allclose(got, 10 * np.log10(lin.sum(axis=0)), atol=1e-4)
+    d3 = d.reshape(2, 2500, 96)
+    got = iqw.dBlinmean(_dev(d3, cuda_device), axis=1).cpu().numpy()
+    np.testing.assert_allclose(got, 10 * np.log10((10.0 ** (d3.astype(np.float64) / 10)).mean(axis=1)), atol=1e-4)
+    got = iqw.dBlinmean(_dev(d[:, 0].copy(), cuda_device))
+    assert got.shape == () and float(got) == pytest.approx(10 * np.log10(lin[:, 0].mean()), abs=1e-4)
+    with pytest.raises(NotImplementedError):
+        iqw.dBlinmean(_dev(d, cuda_device), axis=1)

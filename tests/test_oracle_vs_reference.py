@@ -83,3 +83,20 @@ def test_error_paths_match():
             fn(x, 1.0, 300.0)
         with pytest.raises(ValueError):
             fn(x, 1.0, 100.0, kind='bogus')
+
+
+def test_elementwise_transforms_match_reference():
+    """powtodB / dBtopow / envtopow / envtodB restatements vs the unmodified reference (generic
+    array branch, power_analysis.py:196-204, 226-229, 251-255, 286-296)"""
+    pa = ref.power_analysis
+    rng = np.random.default_rng(9)
+    p = rng.exponential(1e-3, 5000).astype(np.float32)
+    z = (rng.standard_normal(5000) + 1j * rng.standard_normal(5000)).astype(np.complex64)
+    d = rng.uniform(-100, 20, 5000).astype(np.float32)
+    assert np.array_equal(orc.powtodB(p.copy()), pa.powtodB(p.copy()))
+    assert np.array_equal(orc.powtodB(p.copy(), eps=1e-9), pa.powtodB(p.copy(), eps=1e-9))
+    assert np.array_equal(orc.powtodB_noabs(p), pa.powtodB(p.copy(), abs=False))
+    assert np.array_equal(orc.dBtopow(d), pa.dBtopow(d.copy()))
+    assert np.array_equal(orc.envtopow(z), pa.envtopow(z.copy()))
+    assert np.array_equal(orc.envtodB(z), pa.envtodB(z.copy()))
+    assert np.array_equal(orc.envtodB(p, abs=False, eps=1e-6), pa.envtodB(p.copy(), abs=False, eps=1e-6))
