@@ -13,10 +13,10 @@ from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is a
 from . import fourier, power_analysis, distributed
 from .fourier import (stft, spectrogram, power_spectral_density, persistence_spectrum, fftfreq,
                       get_window, equivalent_noise_bandwidth, time_statistics)
-from .power_analysis import (iq_to_bin_power, powtodB, dBtopow, envtopow, envtodB, dBlinmean, dBlinsum)
+from .power_analysis import (iq_to_bin_power, iq_to_cyclic_power, powtodB, dBtopow, envtopow, envtodB, dBlinmean, dBlinsum)
 
 __version__ = '0.1.0'
 __all__ = ['fourier', 'power_analysis', 'distributed', 'stft', 'spectrogram', 'power_spectral_density',
            'persistence_spectrum', 'fftfreq', 'get_window', 'equivalent_noise_bandwidth',
-           'time_statistics', 'iq_to_bin_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean',
+           'time_statistics', 'iq_to_bin_power', 'iq_to_cyclic_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean',
            'dBlinsum']

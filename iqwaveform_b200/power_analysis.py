@@ -13,7 +13,7 @@ import torch
 from . import _arrays, _lib, _plan
 from .fourier import _stream_ptr, time_statistics
 
-__all__ = ['iq_to_bin_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean', 'dBlinsum']
+__all__ = ['iq_to_bin_power', 'iq_to_cyclic_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean', 'dBlinsum']
 
 _DIRECT = {'mean': 'mean', 'rms': 'mean', 'max': 'max', 'peak': 'max', 'min': 'min'}
 
@@ -83,6 +83,47 @@ def iq_to_bin_power(iq, Ts: float, Tbin: float, randomize: bool = False, kind='m
             ctypes.c_void_p(pt.data_ptr()), _stream_ptr(dev)))
         time_statistics(pt, [kind], dB=False, out=out.view(C, 1, n_bins))
     return res.give_back(_arrays.restore_layout(out, lead, trail, 1))
+
+
+_CYCLE_STATS = ('min', 'max', 'peak', 'mean', 'rms', 'median')
+
+
+def iq_to_cyclic_power(x, Ts: float, detector_period: float, cyclic_period: float, truncate=False,
+                       detectors=('rms', 'peak'), cycle_stats=('min', 'mean', 'max'), axis=0):
+    """time series of periodic frame power statistics (power_analysis.py:388-493): detector power
+    on bins of `detector_period` (the bin-power kernel), folded on `cyclic_period`, then a statistic
+    over the cycles for every bin of the cycle (the time-statistics kernel on the
+    (channels, cycles, bins-per-cycle) view -- no data is moved in between).
+
+    Supported layouts: (channels, time) with axis=1 -- the one the reference supports (it tests
+    ``power_shape[1]``, line 454) -- and 1-D captures.  Returns {detector: {statistic: array}}."""
+    if detectors is None:
+        raise ValueError('supply detectors argument to evaluate binned power from time domain IQ')
+    if _plan.isroundmod(cyclic_period, detector_period, atol=1e-6):
+        nbins = round(cyclic_period / detector_period)
+    else:
+        raise ValueError('cyclic period must be positive integer multiple of the detector period')
+    for k in cycle_stats:
+        if k not in _CYCLE_STATS:
+            raise ValueError(f'kind argument must be one of {list(_CYCLE_STATS)}')
+    shape = getattr(x, 'shape', None)
+    if shape is None:
+        raise TypeError('unrecognized object type')
+    ax = axis + len(shape) if axis < 0 else axis
+    if not ((len(shape) == 1 and ax == 0) or (len(shape) == 2 and ax == 1)):
+        raise NotImplementedError('iq_to_cyclic_power is built for (channels, time) axis=1 and 1-D captures')
+    xd, res = _arrays.to_device(x)
+    ret = {}
+    for d in detectors:
+        p = iq_to_bin_power(xd, Ts, detector_period, kind=d, truncate=truncate, axis=ax)     # (C, n_bins) | (n_bins,)
+        n_det = p.shape[-1]
+        if nbins < 1 or n_det % nbins != 0:
+            raise ValueError('pass truncate=True to allow truncation to align with cyclic windows')
+        p3 = p.reshape(-1, n_det // nbins, nbins)
+        stats = time_statistics(p3, list(cycle_stats), dB=False)                            # (C, nstat, nbins)
+        ret[d] = {k: res.give_back(stats[:, i].reshape(p.shape[:-1] + (nbins,)))
+                  for i, k in enumerate(cycle_stats)}
+    return ret
 
 
 # ---------------------------------------------------------------------------------------------

@@ -82,3 +82,23 @@ def test_dBlinmean_dBlinsum(cuda_device):
     assert got.shape == () and float(got) == pytest.approx(10 * np.log10(lin[:, 0].mean()), abs=1e-4)
     with pytest.raises(NotImplementedError):
         iqw.dBlinmean(_dev(d, cuda_device), axis=1)
+
+
+def test_iq_to_cyclic_power(cuda_device):
+    from oracle.make_golden import synth
+    x = synth(12, (3, 60000))
+    kw = dict(Ts=1e-6, detector_period=1e-5, cyclic_period=1e-3)
+    want = orc.iq_to_cyclic_power(x, axis=1, **kw)
+    got = iqw.iq_to_cyclic_power(_dev(x, cuda_device), axis=1, **kw)
+    for d in ('rms', 'peak'):
+        for k in ('min', 'mean', 'max'):
+            g = got[d][k].cpu().numpy()
+            assert g.shape == want[d][k].shape == (3, 100)
+            np.testing.assert_allclose(g, want[d][k], rtol=3e-6)
+    got1 = iqw.iq_to_cyclic_power(x[0], **kw)                 # 1-D numpy in -> numpy out
+    assert isinstance(got1['rms']['mean'], np.ndarray)
+    np.testing.assert_allclose(got1['peak']['max'], want['peak']['max'][0], rtol=3e-6)
+    with pytest.raises(ValueError):
+        iqw.iq_to_cyclic_power(_dev(x, cuda_device), axis=1, Ts=1e-6, detector_period=1e-5, cyclic_period=1.05e-4)
+    with pytest.raises(ValueError):
+        iqw.iq_to_cyclic_power(_dev(x, cuda_device), axis=1, Ts=1e-6, detector_period=1e-5, cyclic_period=7e-4)

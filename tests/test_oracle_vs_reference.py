@@ -100,3 +100,14 @@ def test_elementwise_transforms_match_reference():
     assert np.array_equal(orc.envtopow(z), pa.envtopow(z.copy()))
     assert np.array_equal(orc.envtodB(z), pa.envtodB(z.copy()))
     assert np.array_equal(orc.envtodB(p, abs=False, eps=1e-6), pa.envtodB(p.copy(), abs=False, eps=1e-6))
+
+
+def test_iq_to_cyclic_power_matches_reference():
+    x = synth(12, (3, 60000))
+    kw = dict(Ts=1e-6, detector_period=1e-5, cyclic_period=1e-3)
+    want = ref.power_analysis.iq_to_cyclic_power(x.copy(), axis=1, **kw)
+    got = orc.iq_to_cyclic_power(x.copy(), axis=1, **kw)
+    assert set(got) == set(want) == {'rms', 'peak'}
+    for d in want:
+        for k in want[d]:
+            assert np.array_equal(got[d][k], want[d][k]), (d, k)
