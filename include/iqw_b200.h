@@ -161,8 +161,9 @@ int iqw_debug_set_sample_margin(double sigmas, int extra_ranks);
  * matrix, [2] ranks whose bracket missed, [3] brackets of columns whose candidate lists
  * overflowed, [4]/[5] brackets handed from the candidate lists back to the matrix passes (heavy
  * ties), [6] inconsistent candidate lists (a bug if ever non-zero), [7] brackets settled from the
- * candidate lists alone (the fast path). */
-int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out8);
+ * candidate lists alone (the fast path), [8] 1 if the bracket pass compared order-preserving keys
+ * instead of raw float bits (some bracket bound was negative), [9..15] reserved. */
+int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out16);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement aid (no reference counterpart): when enabled, every kernel launch of the library is

@@ -1619,11 +1619,11 @@ extern "C" int iqw_debug_set_sample_margin(double sigmas, int extra) {
     return IQW_OK;
 }
 
-extern "C" int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out8) {
-    if (!d_workspace || !host_out8 || n_cols < 1) return fail(IQW_ERR_INVALID, "bad argument");
+extern "C" int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out16) {
+    if (!d_workspace || !host_out16 || n_cols < 1) return fail(IQW_ERR_INVALID, "bad argument");
     Work w{};
     carve_work(const_cast<void*>(d_workspace), n_cols, 0, 0, &w);
-    IQW_CUDA_OK(cudaMemcpy(host_out8, w.pending, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    IQW_CUDA_OK(cudaMemcpy(host_out16, w.pending, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return IQW_OK;
 }
 

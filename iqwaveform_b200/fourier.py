@@ -206,10 +206,10 @@ def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25
         if sub is not out:
             out[:, g, :] = sub
         if counters is not None:      # test aid: path counters of the last channel (synchronises)
-            c8 = (ctypes.c_uint32 * 8)()
-            _lib.check(_lib.lib.iqw_debug_time_stats_counters(ctypes.c_void_p(ws.data_ptr()), nb, c8))
+            c16 = (ctypes.c_uint32 * 16)()
+            _lib.check(_lib.lib.iqw_debug_time_stats_counters(ctypes.c_void_p(ws.data_ptr()), nb, c16))
             counters.append(dict(zip(('refine', 'collect', 'missed_ranks', 'overflowed', 'select_to_collect',
-                                      'select_to_refine', 'inconsistent', 'selected'), list(c8))))
+                                      'select_to_refine', 'inconsistent', 'selected', 'key_mode'), list(c16))))
     return out
 
 

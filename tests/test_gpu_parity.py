@@ -287,6 +287,41 @@ def test_sampled_path_is_exact_even_when_brackets_miss(cuda_device, sigmas, extr
     assert np.array_equal(got[:, 4], a.min(axis=1)) and np.array_equal(got[:, 5], a.max(axis=1))
 
 
+def test_long_path_with_many_brackets(cuda_device):
+    """8 well separated single-rank statistics on a long matrix through the C-ABI: 8 brackets -> the
+    M = 8 instantiations of the bracket pass (generic C++ body) and of select; negative data -> key
+    mode instead of raw bits.  Then 3 quantiles of non-negative data: raw-bit mode."""
+    import ctypes
+    from iqwaveform_b200 import _lib
+    rng = np.random.default_rng(5)
+    T, nb = 50001, 130
+    a = rng.standard_normal((1, T, nb)).astype(np.float32)
+    a[0, :, 1] = np.abs(a[0, :, 1])
+    ranks = [500, 6000, 12000, 20000, 27000, 34000, 42000, 49500]
+    reqs = (_lib.iqw_stat * 8)()
+    for r, k in zip(reqs, ranks):
+        r.kind, r.rank_lo, r.rank_hi, r.gamma = _lib.STAT_QUANTILE, k, k, 0.0
+    ad = dev_of(a, cuda_device)
+    out = torch.empty((1, 8, nb), dtype=torch.float32, device=cuda_device)
+    nws = _lib.lib.iqw_time_stats_workspace_bytes(1, T, nb, 8)
+    ws = torch.empty(nws, dtype=torch.uint8, device=cuda_device)
+    _lib.check(_lib.lib.iqw_time_stats_f32(ctypes.c_void_p(ad.data_ptr()), 1, T, nb, T * nb, reqs, 8, 0, 0.0,
+                                           ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), nws,
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    c16 = (ctypes.c_uint32 * 16)()
+    _lib.check(_lib.lib.iqw_debug_time_stats_counters(ctypes.c_void_p(ws.data_ptr()), nb, c16))
+    srt = np.sort(a[0], axis=0)
+    assert np.array_equal(out.cpu().numpy()[0], srt[ranks])
+    assert c16[7] >= 8 * nb - 16 and c16[6] == 0 and c16[8] == 1        # selected, inconsistent, key mode
+    # non-negative data, 3 brackets: raw-bit mode, everything settled from the candidate lists
+    p = np.abs(a)
+    cnt = []
+    got = iqw.time_statistics(dev_of(p, cuda_device), [0.1, 0.5, 0.9], dB=False, counters=cnt).cpu().numpy()
+    want = np.quantile(p, np.array([0.1, 0.5, 0.9], dtype=np.float32), axis=1)
+    assert np.array_equal(got, np.moveaxis(want, 0, 1))
+    assert cnt[0]['key_mode'] == 0 and cnt[0]['refine'] == 0 and cnt[0]['inconsistent'] == 0
+
+
 def test_time_statistics_dB_is_monotone_image(cuda_device):
     rng = np.random.default_rng(2)
     p = rng.exponential(1e-4, (1, 20000, 96)).astype(np.float32)
