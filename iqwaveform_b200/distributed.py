@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ['channel_shard', 'frame_shard', 'bin_shard', 'gather_rows', 'persistence_spectrum_sharded',
-           'spectrogram_time_sharded', 'iq_to_bin_power_sharded']
+           'persistence_spectrum_time_sharded', 'spectrogram_time_sharded', 'iq_to_bin_power_sharded']
 
 
 def _split(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -127,6 +127,45 @@ def persistence_spectrum_sharded(x_local, *, n_channels: int, group=None, comput
         raise ValueError('every rank needs at least one channel (use a sub-group otherwise)')
     out = torch.as_tensor(out)
     return gather_rows(out, [len(channel_shard(n_channels, world, r)) for r in range(world)], 0, group)
+
+
+_REDUCIBLE = {'mean': 'sum', 'rms': 'sum', 'max': 'max', 'peak': 'max', 'min': 'min'}
+
+
+def persistence_spectrum_time_sharded(x_halo, *, n_samples: int, fs: float, resolution: float,
+                                      fractional_overlap=0, statistics, group=None,
+                                      compute: Callable | None = None, **kw):
+    """time-sharded persistence spectrum of ONE long 1-D capture for the statistics that combine
+    with a single exchange: 'mean'/'rms' (frame-count-weighted all_reduce SUM of the per-rank
+    means, taken over dB values when dB=True, like the reference), 'max'/'peak', 'min'
+    (all_reduce MAX / MIN).  `x_halo` holds this rank's samples [shard.sample0, shard.sample1).
+    Exact quantiles across time shards would need a candidate exchange per column and are not
+    built: shard by channel instead (`persistence_spectrum_sharded`)."""
+    for s in statistics:
+        if s not in _REDUCIBLE:
+            raise NotImplementedError(
+                f'statistic {s!r}: only mean/rms/max/peak/min combine across time shards; shard by channel')
+    if compute is None:
+        from .fourier import persistence_spectrum as compute
+    world, rank = _world(group)
+    nfft = round(fs / resolution)
+    noverlap = round(fractional_overlap * nfft)
+    sh = frame_shard(n_samples, nfft, noverlap, world, rank)
+    if x_halo.shape[-1] != sh.sample1 - sh.sample0:
+        raise ValueError(f'rank {rank} expects {sh.sample1 - sh.sample0} samples, got {x_halo.shape[-1]}')
+    local = torch.as_tensor(compute(x_halo, fs=fs, resolution=resolution, fractional_overlap=fractional_overlap,
+                                    statistics=list(statistics), axis=0, **kw)).clone()      # (nstat, nbins)
+    if world == 1:
+        return local
+    n_local = sh.frame1 - sh.frame0
+    for i, s in enumerate(statistics):
+        row = local[i]
+        if _REDUCIBLE[s] == 'sum':
+            row.mul_(n_local / sh.n_frames)
+            dist.all_reduce(row, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(row, op=dist.ReduceOp.MAX if _REDUCIBLE[s] == 'max' else dist.ReduceOp.MIN, group=group)
+    return local
 
 
 def spectrogram_time_sharded(x_halo, *, n_samples: int, nperseg: int, noverlap: int = 0, group=None,

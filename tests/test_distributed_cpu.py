@@ -85,6 +85,21 @@ def _worker(rank, world, port, out_dir):
                                            kind=kind, compute=lambda a, *p, **k: orc.iq_to_bin_power(a.numpy(), *p, **k))
             want = orc.iq_to_bin_power(x2, Ts, Tbin, kind=kind, truncate=True)
             assert np.array_equal(pw.numpy(), want)
+        # --- time-sharded persistence spectrum, reducible statistics (one all_reduce each) ---
+        N = 70001
+        x3 = synth(6, (N,))
+        pk = dict(fs=1e6, window='hann', resolution=1e6 / 256, fractional_overlap=0.5, dB=True)
+        stats = ['mean', 'max', 'min', 'peak']
+        fsh = D.frame_shard(N, 256, 128, world, rank)
+        got = D.persistence_spectrum_time_sharded(
+            torch.from_numpy(x3[fsh.sample0:fsh.sample1]), n_samples=N, statistics=stats,
+            compute=lambda a, **k: orc.persistence_spectrum(a.numpy(), **k), **pk)
+        want = orc.persistence_spectrum(x3, statistics=stats, axis=0, **pk)
+        assert np.array_equal(got.numpy()[1:], want[1:])                      # max / min / peak: exact
+        np.testing.assert_allclose(got.numpy()[0], want[0], atol=1e-3)        # mean of dB: fp32 summation order
+        with pytest.raises(NotImplementedError):
+            D.persistence_spectrum_time_sharded(torch.from_numpy(x3[fsh.sample0:fsh.sample1]), n_samples=N,
+                                                statistics=[0.5], **pk)
         open(os.path.join(out_dir, f'ok{rank}'), 'w').close()
     finally:
         dist.destroy_process_group()

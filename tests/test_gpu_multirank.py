@@ -1,0 +1,60 @@
+"""N > 1 on real GPUs (skipped with fewer than 2 devices): one process per GPU over NCCL; the
+channel-, frame- and bin-sharded results equal the single-GPU ones bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import iqwaveform_b200 as iqw
+    from iqwaveform_b200 import distributed as D
+    from oracle.make_golden import synth
+
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        C, N = 2 * world + 1, 1 << 18
+        x = torch.from_numpy(synth(21, (C, N))).to(dev)
+        kw = dict(fs=1e6, window='hann', resolution=1e6 / 1024, fractional_overlap=0.5,
+                  statistics=[0.1, 0.5, 0.999, 'max', 'mean'], dB=True)
+        mine = D.channel_shard(C, world, rank)
+        full = D.persistence_spectrum_sharded(x[mine.start:mine.stop], n_channels=C, **kw)
+        single = iqw.persistence_spectrum(x, axis=1, **kw)
+        assert torch.equal(full, single)
+
+        x1 = x[0]
+        sh = D.frame_shard(N, 2048, 1024, world, rank)
+        spg = D.spectrogram_time_sharded(x1[sh.sample0:sh.sample1].contiguous(), n_samples=N, nperseg=2048,
+                                         noverlap=1024, gather=True, fs=1e6, window='blackmanharris')
+        assert torch.equal(spg, iqw.spectrogram(x1, fs=1e6, window='blackmanharris', nperseg=2048, noverlap=1024,
+                                                return_axis_arrays=False))
+        bs = D.bin_shard(N, 1000, world, rank)
+        pw = D.iq_to_bin_power_sharded(x1[bs.sample0:bs.sample1].contiguous(), 1e-6, 1e-3, n_samples=N, kind='peak')
+        assert torch.equal(pw, iqw.iq_to_bin_power(x1, 1e-6, 1e-3, kind='peak', truncate=True))
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_equals_single_gpu_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs at least 2 GPUs')
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(world))
