@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _arrays, _lib, _plan
+from .util import Domain, get_input_domain
 from ._plan import INF
 
 __all__ = ['stft', 'spectrogram', 'power_spectral_density', 'persistence_spectrum', 'fftfreq',
@@ -229,9 +230,15 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
     else:
         raise ValueError(
             '(1-fractional_window) * (sample_rate/frequency_resolution) must be a counting number')
-    _check_window_arg(window)
     statistics = list(statistics)
     _plan.stat_requests(statistics, 2)          # validates names before any device work
+    domain = get_input_domain()
+    if domain == Domain.FREQUENCY:
+        return _psd_from_stft(x, fs=fs, nfft=nfft, bandwidth=bandwidth, statistics=statistics,
+                              truncate=truncate, dB=dB, axis=axis)
+    if domain != Domain.TIME:
+        raise ValueError(f'unsupported persistence spectrum domain "{domain}"')
+    _check_window_arg(window)
     _host_checks(x, axis, nfft, noverlap, True)
 
     xd, res = _arrays.to_device(x)
@@ -251,6 +258,29 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
         scratch = p
         time_statistics(p, statistics, dB=bool(dB), eps=1e-25, out=out[c:c + 1])
     return res.give_back(_arrays.restore_layout(out, lead, trail, 2))
+
+
+def _psd_from_stft(X, *, fs, nfft, bandwidth, statistics, truncate, dB, axis):
+    """``Domain.FREQUENCY`` branch (fourier.py:1277-1285, 1303-1307): X is an STFT (C, T, nfft),
+    complex64, time on `axis` = 1.  dB is envtodB(X, eps=1e-25) = 20*log10(|X| + 1e-25), otherwise
+    envtopow; then the statistics over time.  The band trim is applied to the result rows (the
+    statistics of a bin do not depend on the other bins), so nothing is copied."""
+    from .power_analysis import _elementwise
+    shape = getattr(X, 'shape', None)
+    if shape is None:
+        raise TypeError('unrecognized object type')
+    ax = axis + len(shape) if axis < 0 else axis
+    if len(shape) != 3 or ax != 1 or shape[2] != nfft:
+        raise ValueError(f'frequency-domain input must be (channels, frames, {nfft}) with the time axis 1')
+    Xd, res = _arrays.to_device(X)
+    if Xd.dtype != torch.complex64:
+        raise NotImplementedError(f'only complex64 STFTs are built (got {Xd.dtype})')
+    spg = _elementwise(Xd, _lib.EW_ENVTODB if dB else _lib.EW_ENVTOPOW, eps=1e-25 if dB else 0.0)
+    out = time_statistics(spg, statistics, dB=False)
+    if truncate and bandwidth != INF:
+        ilo, ihi = _plan.freq_band_edges(nfft, 1.0 / fs, -bandwidth / 2, +bandwidth / 2)
+        out = out[:, :, ilo:ihi].contiguous()
+    return res.give_back(out)
 
 
 persistence_spectrum = power_spectral_density

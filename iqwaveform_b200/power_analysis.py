@@ -12,6 +12,7 @@ import torch
 
 from . import _arrays, _lib, _plan
 from .fourier import _stream_ptr, time_statistics
+from .util import Domain, get_input_domain
 
 __all__ = ['iq_to_bin_power', 'iq_to_cyclic_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean', 'dBlinsum']
 
@@ -97,7 +98,18 @@ def iq_to_cyclic_power(x, Ts: float, detector_period: float, cyclic_period: floa
 
     Supported layouts: (channels, time) with axis=1 -- the one the reference supports (it tests
     ``power_shape[1]``, line 454) -- and 1-D captures.  Returns {detector: {statistic: array}}."""
-    if detectors is None:
+    domain = get_input_domain()
+    if domain == Domain.TIME_BINNED_POWER:
+        # precalculated binned power: dict keyed by detector (power_analysis.py:438-448)
+        if not isinstance(x, dict):
+            raise TypeError('in time-binned power domain, expected dict input keyed by detector')
+        if detectors is None:
+            detectors = tuple(x.keys())
+        elif set(x.keys()) != set(detectors):
+            raise ValueError('input data keys do not match supplied ')
+    elif domain != Domain.TIME:
+        raise ValueError(f'unsupported cyclic power domain "{domain}"')
+    elif detectors is None:
         raise ValueError('supply detectors argument to evaluate binned power from time domain IQ')
     if _plan.isroundmod(cyclic_period, detector_period, atol=1e-6):
         nbins = round(cyclic_period / detector_period)
@@ -106,16 +118,24 @@ def iq_to_cyclic_power(x, Ts: float, detector_period: float, cyclic_period: floa
     for k in cycle_stats:
         if k not in _CYCLE_STATS:
             raise ValueError(f'kind argument must be one of {list(_CYCLE_STATS)}')
-    shape = getattr(x, 'shape', None)
+    first = x[detectors[0]] if domain == Domain.TIME_BINNED_POWER else x
+    shape = getattr(first, 'shape', None)
     if shape is None:
         raise TypeError('unrecognized object type')
     ax = axis + len(shape) if axis < 0 else axis
     if not ((len(shape) == 1 and ax == 0) or (len(shape) == 2 and ax == 1)):
         raise NotImplementedError('iq_to_cyclic_power is built for (channels, time) axis=1 and 1-D captures')
-    xd, res = _arrays.to_device(x)
+    if domain == Domain.TIME:
+        xd, res = _arrays.to_device(x)
     ret = {}
     for d in detectors:
-        p = iq_to_bin_power(xd, Ts, detector_period, kind=d, truncate=truncate, axis=ax)     # (C, n_bins) | (n_bins,)
+        if domain == Domain.TIME:
+            p = iq_to_bin_power(xd, Ts, detector_period, kind=d, truncate=truncate, axis=ax)  # (C, n_bins) | (n_bins,)
+        else:
+            p, res = _arrays.to_device(x[d])
+            if p.dtype != torch.float32:
+                raise NotImplementedError(f'only float32 binned power is built (got {p.dtype})')
+            p = p.contiguous()
         n_det = p.shape[-1]
         if nbins < 1 or n_det % nbins != 0:
             raise ValueError('pass truncate=True to allow truncation to align with cyclic windows')

@@ -102,3 +102,37 @@ def test_iq_to_cyclic_power(cuda_device):
         iqw.iq_to_cyclic_power(_dev(x, cuda_device), axis=1, Ts=1e-6, detector_period=1e-5, cyclic_period=1.05e-4)
     with pytest.raises(ValueError):
         iqw.iq_to_cyclic_power(_dev(x, cuda_device), axis=1, Ts=1e-6, detector_period=1e-5, cyclic_period=7e-4)
+
+
+def test_input_domains(cuda_device):
+    """set_input_domain('frequency') / ('time_binned_power') branches"""
+    from oracle.make_golden import synth
+    x = synth(8, (2, 40000))
+    _, _, X = orc.stft(x, fs=1e6, window='hann', nperseg=256, noverlap=128, axis=1, norm='power')
+    stats = [0.1, 0.5, 'mean', 'max']
+    for dB in (True, False):
+        for bw in (float('inf'), 0.5e6):
+            want = orc.persistence_spectrum_from_stft(X, fs=1e6, bandwidth=bw, resolution=1e6 / 256,
+                                                      fractional_overlap=0.5, statistics=stats, dB=dB, axis=1)
+            with iqw.set_input_domain('frequency'):
+                got = iqw.power_spectral_density(_dev(X, cuda_device), fs=1e6, bandwidth=bw, window='hann',
+                                                 resolution=1e6 / 256, fractional_overlap=0.5,
+                                                 statistics=stats, dB=dB, axis=1).cpu().numpy()
+            assert got.shape == want.shape
+            if dB:
+                assert np.max(np.abs(got - want)) <= 1e-4
+            else:
+                np.testing.assert_allclose(got, want, rtol=5e-6)
+    assert iqw.get_input_domain() == iqw.Domain.TIME
+    # binned power in, cyclic statistics out
+    kw = dict(Ts=1e-6, detector_period=1e-5, cyclic_period=1e-3)
+    binned = {d: orc.iq_to_bin_power(x, 1e-6, 1e-5, kind=d, axis=1) for d in ('rms', 'peak')}
+    want = orc.iq_to_cyclic_power(x, axis=1, **kw)
+    with iqw.set_input_domain(iqw.Domain.TIME_BINNED_POWER):
+        got = iqw.iq_to_cyclic_power({d: _dev(v, cuda_device) for d, v in binned.items()}, axis=1,
+                                     detectors=None, **kw)
+        with pytest.raises(TypeError):
+            iqw.iq_to_cyclic_power(_dev(x, cuda_device), axis=1, **kw)
+    for d in ('rms', 'peak'):
+        for k in ('min', 'mean', 'max'):
+            np.testing.assert_allclose(got[d][k].cpu().numpy(), want[d][k], rtol=3e-6)

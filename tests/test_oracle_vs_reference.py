@@ -111,3 +111,20 @@ def test_iq_to_cyclic_power_matches_reference():
     for d in want:
         for k in want[d]:
             assert np.array_equal(got[d][k], want[d][k]), (d, k)
+
+
+def test_frequency_domain_persistence_matches_reference():
+    """Domain.FREQUENCY branch (fourier.py:1277-1285, 1303-1307): named rows against the reference
+    (its quantile rows are uninitialised memory)"""
+    x = synth(8, (2, 40000))
+    _, _, X = orc.stft(x, fs=1e6, window='hann', nperseg=256, noverlap=128, axis=1, norm='power')
+    stats = ['mean', 'max', 'min']
+    for dB in (True, False):
+        for bw in (float('inf'), 0.5e6):
+            with ref.util.set_input_domain('frequency'):
+                want = ref.fourier.power_spectral_density(X.copy(), fs=1e6, bandwidth=bw, window='hann',
+                                                          resolution=1e6 / 256, fractional_overlap=0.5,
+                                                          statistics=stats, dB=dB, axis=1)
+            got = orc.persistence_spectrum_from_stft(X.copy(), fs=1e6, bandwidth=bw, resolution=1e6 / 256,
+                                                     fractional_overlap=0.5, statistics=stats, dB=dB, axis=1)
+            assert got.shape == want.shape and np.array_equal(got, want), (dB, bw)
