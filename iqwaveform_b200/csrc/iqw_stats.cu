@@ -580,33 +580,42 @@ refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long 
               Work w) {
     if (*w.pending == 0) return;
     extern __shared__ uint16_t hist[];   // [M*32][kBX]
-    const long long col = (long long)blockIdx.x * kBX + threadIdx.x;
     const int t = threadIdx.x;
-    int active = 0;
-    IvRegs<M> iv;
-    iv.load(w, col, col < cols, IV_REFINE, active);
-    for (int i = t; i < M * kNSub * kBX; i += kBX) hist[i] = 0;
-    if (!__syncthreads_or(active)) return;
-    if (!active) return;
-
+    const long long col_tiles = (cols + kBX - 1) / kBX;
     const long long i0 = (long long)blockIdx.y * rows_per_split;
     const long long i1 = min(rm.n, i0 + rows_per_split);
-    auto visit = [&](float f) {
-        const uint32_t k = float_to_key(f);
-        uint32_t kl, kh, sh;
-        const int v = iv.find(k, kl, kh, sh);
-        if (v >= 0 && k <= kh && sh < 32u) hist[(v * kNSub + ((k - kl) >> sh)) * kBX + t] += 1;
-    };
-    IQW_STREAM(rm.step != 1, p, cols, col, rm, i0, i1, visit);
+    // a CTA owns the row range of blockIdx.y and walks column tiles blockIdx.x, + gridDim.x, ...;
+    // tiles without a pending interval cost one look at their interval lists.  (After the long
+    // path only a few tiles are ever pending, so its launch uses few tile slots and many row
+    // splits: the whole GPU then works on the one tile that needs it.)
+    for (long long tile = blockIdx.x; tile < col_tiles; tile += gridDim.x) {
+        const long long col = tile * kBX + t;
+        int active = 0;
+        IvRegs<M> iv;
+        iv.load(w, col, col < cols, IV_REFINE, active);
+        if (!__syncthreads_or(active)) continue;
+        for (int i = t; i < M * kNSub * kBX; i += kBX) hist[i] = 0;
+        __syncthreads();
+        if (active) {
+            auto visit = [&](float f) {
+                const uint32_t k = float_to_key(f);
+                uint32_t kl, kh, sh;
+                const int v = iv.find(k, kl, kh, sh);
+                if (v >= 0 && k <= kh && sh < 32u) hist[(v * kNSub + ((k - kl) >> sh)) * kBX + t] += 1;
+            };
+            IQW_STREAM(rm.step != 1, p, cols, col, rm, i0, i1, visit);
 
-    uint32_t* g = w.hist1 + col * (kMaxRanks * kNSub);
+            uint32_t* g = w.hist1 + col * (kMaxRanks * kNSub);
 #pragma unroll
-    for (int v = 0; v < M; ++v) {
-        if (iv.shift[v] >= 32u) continue;
-        for (int b = 0; b < kNSub; ++b) {
-            const uint32_t c = hist[(v * kNSub + b) * kBX + t];
-            if (c) atomicAdd(g + v * kNSub + b, c);
+            for (int v = 0; v < M; ++v) {
+                if (iv.shift[v] >= 32u) continue;
+                for (int b = 0; b < kNSub; ++b) {
+                    const uint32_t c = hist[(v * kNSub + b) * kBX + t];
+                    if (c) atomicAdd(g + v * kNSub + b, c);
+                }
+            }
         }
+        __syncthreads();        // the private counters are zeroed again for the next tile
     }
 }
 
@@ -790,26 +799,28 @@ __global__ void __launch_bounds__(kBX)
 collect_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
                Work w) {
     if (w.pending[1] == 0) return;
-    const long long col = (long long)blockIdx.x * kBX + threadIdx.x;
-    int active = 0;
-    IvRegs<M> iv;
-    iv.load(w, col, col < cols, IV_COLLECT, active);
-    if (!__syncthreads_or(active)) return;
-    if (!active) return;
-
+    const long long col_tiles = (cols + kBX - 1) / kBX;
     const long long i0 = (long long)blockIdx.y * rows_per_split;
     const long long i1 = min(rm.n, i0 + rows_per_split);
-    auto visit = [&](float f) {
-        const uint32_t k = float_to_key(f);
-        uint32_t kl, kh, sh;
-        const int v = iv.find(k, kl, kh, sh);
-        if (v >= 0 && k <= kh && sh < 32u) {
-            const long long x = col * kMaxRanks + v;
-            const uint32_t pos = atomicAdd(w.cursor + x, 1u);
-            if (pos < (uint32_t)kCap) w.cand[x * kCap + pos] = k;
-        }
-    };
-    IQW_STREAM(rm.step != 1, p, cols, col, rm, i0, i1, visit);
+    for (long long tile = blockIdx.x; tile < col_tiles; tile += gridDim.x) {     // see refine_kernel
+        const long long col = tile * kBX + threadIdx.x;
+        int active = 0;
+        IvRegs<M> iv;
+        iv.load(w, col, col < cols, IV_COLLECT, active);
+        if (!__syncthreads_or(active)) continue;
+        if (!active) continue;
+        auto visit = [&](float f) {
+            const uint32_t k = float_to_key(f);
+            uint32_t kl, kh, sh;
+            const int v = iv.find(k, kl, kh, sh);
+            if (v >= 0 && k <= kh && sh < 32u) {
+                const long long x = col * kMaxRanks + v;
+                const uint32_t pos = atomicAdd(w.cursor + x, 1u);
+                if (pos < (uint32_t)kCap) w.cand[x * kCap + pos] = k;
+            }
+        };
+        IQW_STREAM(rm.step != 1, p, cols, col, rm, i0, i1, visit);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1696,8 +1707,19 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
             IQW_DISPATCH_G(lp.bp.n_groups, if (int rc = launch_select<M>(s, n_cols, rp, lp, w)) return rc);
             // whatever select could not settle from the lists (missed brackets, overflowed lists,
             // heavy ties) is refined from the matrix; these exit at once when nothing is open
+            // few tile slots x many row splits: when one column misses, the whole GPU reads its tile
             Grid g;
-            if (int rc = plan_grid(n_rows, col_tiles, sms, &g)) return rc;
+            {
+                const long long slots = col_tiles < 4 ? col_tiles : 4;
+                long long splits = (32ll * sms + slots - 1) / slots;
+                long long rps = (n_rows + splits - 1) / splits;
+                if (rps < 4 * kUnroll) rps = 4 * kUnroll;
+                if (rps > 65535) rps = 65535;                         // uint16 counters of refine_kernel
+                splits = (n_rows + rps - 1) / rps;
+                if (splits > 65535) return fail(IQW_ERR_UNSUPPORTED, "too many rows for the split grid");
+                g.grid = dim3((unsigned)slots, (unsigned)splits);
+                g.rows_per_split = rps;
+            }
             IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, n_cols, full, rp, w, cblocks, cthreads, "stats"));
             IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, n_cols, full, w, "stats_collect"));
             { IQW_PROFILE("stats_resolve", s);
