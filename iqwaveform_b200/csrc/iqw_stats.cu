@@ -25,7 +25,7 @@
 //   resolve : bitonic sort of the candidates in shared memory -> key of every target rank
 //   finalize: dB, numpy lerp, mean/max/min, store
 //
-// LONG COLUMNS (rows >= 32768): ONE full read of the matrix instead of four.
+// LONG COLUMNS (rows >= 16384): ONE full read of the matrix instead of four.
 //   A. sample_brackets : a stratified, jittered ROW SAMPLE (<= 8192 rows) of two columns per CTA is
 //      staged in shared memory; a two-level histogram (2048 bins, then 256 sub-bins around each
 //      wanted sample rank) gives, per group of target ranks, a key BRACKET [lo, hi] that holds the
@@ -57,7 +57,7 @@ constexpr int kCap = 2048;         // candidates kept per (column, interval)
 constexpr int kRefineLevels = 7;   // 32 key bits / 5 bits per level
 constexpr int kBX = 128;           // columns (= threads) per CTA in the streaming passes
 constexpr int kUnroll = 8;         // rows in flight per thread
-constexpr long long kSampleMinRows = 32768;   // below this the exact pipeline reads all rows
+constexpr long long kSampleMinRows = 16384;   // below this the exact pipeline reads all rows
 constexpr int kSampleRows = 8192;  // rows of the sample staged in shared memory (per column)
 constexpr int kSampleCols = 2;     // columns per CTA of sample_brackets
 constexpr int kMaxGroups = 8;      // rank groups (brackets) per call on the sampled path
