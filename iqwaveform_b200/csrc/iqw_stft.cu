@@ -53,7 +53,14 @@ struct PassLoop {
             constexpr int E = plan_elems(LOG2N);
             float2 tn[E];
             load_twiddles<LOG2N, P + 1>(tn, tw, ltid);
-            __syncthreads();
+            // only the threads of this frame slot exchange data: a named barrier per slot when a
+            // slot is made of whole warps, a warp barrier when it fits in one warp, the CTA barrier otherwise
+            if constexpr (C::TPF <= 32)
+                __syncwarp();                       // the slot lives inside one warp
+            else if constexpr (C::FPC > 1 && C::TPF % 32 == 0)
+                asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(C::TPF) : "memory");
+            else
+                __syncthreads();
             par ^= 1;
             PassLoop<LOG2N, P + 1>::run(v, bufs, tw, tn, ltid, slot, par);
         }

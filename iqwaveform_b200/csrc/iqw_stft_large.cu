@@ -171,7 +171,8 @@ struct RowPasses {
         if constexpr (!LAST) {
             float2 tn[kRowE];
             load_twiddles<kLog2N2, P + 1>(tn, tw, ltid);
-            __syncthreads();
+            static_assert(kRowTPF <= 32 && 32 % kRowTPF == 0, "a row transform lives inside one warp");
+            __syncwarp();
             par ^= 1;
             RowPasses<P + 1>::run(v, bufs, tw, tn, ltid, slot, par);
         }
