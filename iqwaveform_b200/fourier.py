@@ -107,8 +107,10 @@ def _check_window_arg(window):
 
 def _stft_device(x2: torch.Tensor, *, window, nfft: int, noverlap: int, nzero: int, norm,
                  truncate: bool, mode: int, eps: float = 0.0, bin_lo: int = 0, bin_hi=None,
-                 out: torch.Tensor | None = None) -> torch.Tensor:
-    """(C, N) complex64 on the device -> (C, T, nbins)"""
+                 out: torch.Tensor | None = None, frames: tuple | None = None) -> torch.Tensor:
+    """(C, N) complex64 on the device -> (C, T, nbins).  `frames=(f0, f1)` computes only that frame
+    range (C must be 1) into rows f0..f1 of `out`: used to transform a capture while it is still
+    arriving from the host."""
     if x2.dtype != torch.complex64:
         raise NotImplementedError(f'only complex64 waveforms are built (got {x2.dtype})')
     if nfft < 1 or not 0 <= noverlap < nfft:
@@ -128,13 +130,21 @@ def _stft_device(x2: torch.Tensor, *, window, nfft: int, noverlap: int, nzero: i
         raise ValueError(f'out must be a contiguous {dtype} tensor of shape {(C, T, nb)}')
     if T == 0 or C == 0:
         return out
-    ws_bytes = _lib.lib.iqw_stft_workspace_bytes(nfft, C, T)     # > 0 only for nfft > 8192
+    f0, f1 = (0, T) if frames is None else frames
+    if frames is not None and (C != 1 or not 0 <= f0 <= f1 <= T):
+        raise ValueError('frames=(f0, f1) needs a single channel and 0 <= f0 <= f1 <= T')
+    if f1 == f0:
+        return out
+    nf = f1 - f0
+    esz = 8 if mode == _lib.STFT_COMPLEX else 4
+    ws_bytes = _lib.lib.iqw_stft_workspace_bytes(nfft, C, nf)     # > 0 only for nfft > 8192
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device) if ws_bytes else None
     _lib.check(_lib.lib.iqw_stft_c64(
-        ctypes.c_void_p(x2.data_ptr()), C, N, x2.stride(0) if C > 1 else N,
-        ctypes.c_void_p(w.data_ptr()), nfft, hop, T, mode, eps, bin_lo, bin_hi,
-        ctypes.c_void_p(out.data_ptr()), T * nb, ctypes.c_void_p(ws.data_ptr()) if ws_bytes else None,
-        ws_bytes, _stream_ptr(x2.device)))
+        ctypes.c_void_p(x2.data_ptr() + f0 * hop * 8), C, (nf - 1) * hop + nfft if frames is not None else N,
+        x2.stride(0) if C > 1 else N,
+        ctypes.c_void_p(w.data_ptr()), nfft, hop, nf, mode, eps, bin_lo, bin_hi,
+        ctypes.c_void_p(out.data_ptr() + f0 * nb * esz), T * nb,
+        ctypes.c_void_p(ws.data_ptr()) if ws_bytes else None, ws_bytes, _stream_ptr(x2.device)))
     return out
 
 
@@ -241,12 +251,17 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
     _check_window_arg(window)
     _host_checks(x, axis, nfft, noverlap, True)
 
-    xd, res = _arrays.to_device(x)
-    x2, lead, trail = _arrays.as_channels(xd, axis)
-
     bin_lo, bin_hi = 0, nfft
     if truncate and bandwidth != INF:
         bin_lo, bin_hi = _plan.freq_band_edges(nfft, 1.0 / fs, -bandwidth / 2, +bandwidth / 2)
+
+    host = _host_rows(x, axis)
+    if host is not None and host[0].numel() * 8 >= STREAM_MIN_BYTES:
+        return _psd_from_host(*host, window=window, nfft=nfft, noverlap=noverlap, nzero=nzero,
+                              bin_lo=bin_lo, bin_hi=bin_hi, statistics=statistics, dB=dB)
+
+    xd, res = _arrays.to_device(x)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
 
     C = x2.shape[0]
     out = torch.empty((C, len(statistics), bin_hi - bin_lo), dtype=torch.float32, device=x2.device)
@@ -258,6 +273,74 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
         scratch = p
         time_statistics(p, statistics, dB=bool(dB), eps=1e-25, out=out[c:c + 1])
     return res.give_back(_arrays.restore_layout(out, lead, trail, 2))
+
+
+STREAM_MIN_BYTES = 64 << 20      # host captures at least this large are transformed while they arrive
+STREAM_CHUNKS = 16
+_copy_streams: dict = {}
+
+
+def _host_rows(x, axis):
+    """(rows tensor (C, N) on the host with contiguous rows, kind, squeeze) for a host capture whose
+    time axis is the last one, else None"""
+    if isinstance(x, np.ndarray):
+        kind, t = 'numpy', (torch.from_numpy(x) if x.dtype == np.complex64 else None)
+    elif isinstance(x, torch.Tensor) and not x.is_cuda:
+        kind, t = 'torch_cpu', (x if x.dtype == torch.complex64 else None)
+    else:
+        return None
+    if t is None or t.ndim not in (1, 2):
+        return None
+    ax = axis + t.ndim if axis < 0 else axis
+    if ax != t.ndim - 1 or t.stride(-1) != 1:
+        return None
+    return (t.reshape(1, -1) if t.ndim == 1 else t), kind, t.ndim == 1
+
+
+def _psd_from_host(xh, kind, squeeze, *, window, nfft, noverlap, nzero, bin_lo, bin_hi, statistics, dB):
+    """persistence spectrum of a HOST capture: the host->device copy runs in chunks on a copy stream
+    and the STFT of the frames that are complete follows each chunk on the compute stream, so only the
+    time statistics remain after the last byte has arrived (the copy is the bottleneck: 8 B/sample
+    over PCIe).  Same kernels and frame arithmetic as the device path, hence identical results."""
+    dev = _arrays._device()
+    main = torch.cuda.current_stream(dev)
+    cs = _copy_streams.get(dev.index)
+    if cs is None:
+        cs = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    C, N = xh.shape
+    hop = nfft - noverlap
+    T = _frame_count(N, nfft, noverlap, True)
+    nb = bin_hi - bin_lo
+    out = torch.empty((C, len(statistics), nb), dtype=torch.float32, device=dev)
+    spg = torch.empty((1, T, nb), dtype=torch.float32, device=dev)
+    bufs = [torch.empty((1, N), dtype=torch.complex64, device=dev) for _ in range(min(C, 2))]
+    for b in bufs:
+        b.record_stream(cs)
+    step = -(-N // STREAM_CHUNKS)
+    step = max(nfft, -(-step // hop) * hop)
+    freed = [None, None]                      # event after the last kernel that read bufs[i]
+    for c in range(C):
+        xd = bufs[c % 2]
+        cs.wait_stream(main) if c == 0 else None
+        if freed[c % 2] is not None:
+            cs.wait_event(freed[c % 2])
+        done = 0
+        for s0 in range(0, N, step):
+            s1 = min(N, s0 + step)
+            with torch.cuda.stream(cs):
+                xd[0, s0:s1].copy_(xh[c, s0:s1], non_blocking=True)
+                ev = cs.record_event()
+            main.wait_event(ev)
+            f1 = min(T, (s1 - nfft) // hop + 1) if s1 >= nfft else 0
+            if f1 > done:
+                _stft_device(xd, window=window, nfft=nfft, noverlap=noverlap, nzero=nzero, norm='power',
+                             truncate=True, mode=_lib.STFT_POWER, bin_lo=bin_lo, bin_hi=bin_hi, out=spg,
+                             frames=(done, f1))
+                done = f1
+        freed[c % 2] = main.record_event()
+        time_statistics(spg, statistics, dB=bool(dB), eps=1e-25, out=out[c:c + 1])
+    res = _arrays.Residence(kind)
+    return res.give_back(out[0] if squeeze else out)
 
 
 def _psd_from_stft(X, *, fs, nfft, bandwidth, statistics, truncate, dB, axis):

@@ -367,3 +367,21 @@ def test_bin_power_golden_and_layouts(cuda_device):
     got = iqw.iq_to_bin_power(xd[0, 1:], 1.0, 1537.0, kind='mean', truncate=True).cpu().numpy()
     ref = orc.iq_to_bin_power(a['x'][0, 1:], 1.0, 1537.0, kind='mean', truncate=True)
     np.testing.assert_allclose(got, ref, rtol=2e-6)
+
+
+def test_persistence_streams_host_captures(cuda_device, monkeypatch):
+    """host captures above STREAM_MIN_BYTES are copied in chunks with the STFT following each chunk:
+    same frames, same kernels -> bitwise equal to the device-resident call, for any chunking"""
+    from iqwaveform_b200 import fourier
+    x = synth(31, (3, 300007))
+    kw = dict(fs=1e6, window='hann', resolution=1e6 / 1024, fractional_overlap=0.75,
+              statistics=[0.1, 0.5, 0.999, 'max', 'mean'], axis=1)
+    want = iqw.persistence_spectrum(dev_of(x, cuda_device), **kw).cpu().numpy()
+    monkeypatch.setattr(fourier, 'STREAM_MIN_BYTES', 1)
+    for chunks in (1, 5, 16, 1000):
+        monkeypatch.setattr(fourier, 'STREAM_CHUNKS', chunks)
+        got = iqw.persistence_spectrum(x, **kw)                       # numpy in -> numpy out
+        assert isinstance(got, np.ndarray) and np.array_equal(got, want), chunks
+    pinned = torch.from_numpy(x[0]).pin_memory()
+    got = iqw.persistence_spectrum(pinned, **dict(kw, axis=0))        # 1-D pinned torch in -> CPU torch out
+    assert isinstance(got, torch.Tensor) and not got.is_cuda and np.array_equal(got.numpy(), want[0])
