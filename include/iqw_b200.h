@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IQW_ABI_VERSION 2
+#define IQW_ABI_VERSION 3
 
 typedef enum iqw_status {
     IQW_OK = 0,
@@ -48,7 +48,8 @@ typedef enum iqw_stat_kind {
     IQW_STAT_MEAN = 1,     /* 'mean' and 'rms'                                                    */
     IQW_STAT_MAX = 2,      /* 'max' and 'peak'                                                    */
     IQW_STAT_MIN = 3,
-    IQW_STAT_MEDIAN = 4    /* numpy median: 0.5*(a[(n-1)/2] + a[n/2])                             */
+    IQW_STAT_MEDIAN = 4,   /* numpy median: 0.5*(a[(n-1)/2] + a[n/2])                             */
+    IQW_STAT_ORDER = 5     /* the order statistic a[rank_lo] itself (no interpolation)            */
 } iqw_stat_kind;
 
 /* one requested statistic (one output row).  For QUANTILE the host supplies the float32 index
@@ -145,6 +146,64 @@ typedef enum iqw_ew_op { IQW_EW_POWTODB = 0, IQW_EW_DBTOPOW = 1, IQW_EW_ENVTOPOW
 int iqw_elementwise_f32(int32_t op, const float* d_in, float* d_out, int64_t n, int32_t use_abs, float eps,
                         void* stream);
 int iqw_elementwise_c64(int32_t op, const void* d_in, float* d_out, int64_t n, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Exact order statistics of a float32 matrix whose ROWS are spread over several GPUs (the
+ * time-sharded persistence spectrum; no reference counterpart -- the reference calls np.quantile
+ * on the whole spectrogram in one process, fourier.py:1317-1320).  Most-significant-digit radix
+ * select on order-preserving uint32 keys (key = bits ^ 0x80000000 for non-negative floats,
+ * ~bits for negative ones), 8 bits per level, levels 0..3, inside a key interval [lo, hi] per
+ * column and statistic that the caller seeds with a bracket known to hold the statistic
+ * (0 .. 0xFFFFFFFF always works; a tight bracket makes the passes HBM-bound because only rows
+ * inside the interval touch the histograms):
+ *
+ *   iqw_bracket_collect_f32  ONE pass over this device's rows: rows with key < lo per statistic
+ *                         -> d_below rows 0..n_sel-1; rows inside ANY [lo, hi] are copied to the
+ *                         candidate store in d_workspace; d_below row n_sel counts, per column,
+ *                         the store segments that overflowed (heavy ties): if its sum over the
+ *                         devices is non-zero anywhere, use iqw_radix_count_f32 instead of
+ *                         iqw_candidate_count_f32 below.  n_sel <= 8 per call.
+ *   iqw_candidate_count_f32  like iqw_radix_count_f32, over the candidate store
+ *   iqw_radix_count_f32   counts of THIS device's rows with lo <= key <= hi by key digit
+ *                         (key >> (24 - 8*level)) & 255, per statistic and column; with d_below,
+ *                         also the rows with key < lo.  Both outputs are zeroed by the call.
+ *   (caller)              all_reduce(SUM) of d_counts (and d_below) over the devices holding rows;
+ *                         at level 0 the caller subtracts the summed d_below from d_rank
+ *   iqw_radix_descend     walks the summed counts: the digit that holds the residual rank is
+ *                         appended to the prefix, the rank is made relative to that bucket and
+ *                         [lo, hi] is intersected with the bucket.  After level 3 d_prefix holds
+ *                         the keys of the order statistics.  A rank outside the counted rows ends
+ *                         as the key of NaN.
+ *   iqw_order_stats_finish_f32  dB (optional) of the selected values + numpy 'linear' lerp /
+ *                         median, as the last step of iqw_time_stats_f32 does.
+ *
+ *   d_p        (n_rows, n_cols) float32, C-contiguous; n_rows may be 0
+ *   d_lo,d_hi  (n_sel, n_cols) uint32 keys, in/out of iqw_radix_descend
+ *   d_prefix   (n_sel, n_cols) uint32        d_rank  (n_sel, n_cols) int64, in/out
+ *   d_counts   (n_sel, n_cols, 256) int32    d_below NULL or (n_sel, n_cols) int32
+ *              (iqw_bracket_collect_f32: (n_sel + 1, n_cols), required)
+ *   d_workspace >= iqw_bracket_collect_workspace_bytes(n_rows, n_cols) bytes (about 1/8 of the
+ *              matrix), 256-byte aligned; the same n_rows / n_cols go to iqw_candidate_count_f32
+ *   sel_rank   HOST array: the 0-based global rank each of the n_sel rows of d_keys answers
+ *   stats      HOST array of QUANTILE / MEDIAN requests whose ranks are all in sel_rank
+ *   d_out      (n_stats, n_cols) float32
+ */
+size_t iqw_bracket_collect_workspace_bytes(int64_t n_rows, int64_t n_cols);
+int iqw_bracket_collect_f32(const float* d_p, int64_t n_rows, int64_t n_cols, int32_t n_sel,
+                            const uint32_t* d_lo, const uint32_t* d_hi, int32_t* d_below,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+int iqw_candidate_count_f32(const void* d_workspace, int64_t n_rows, int64_t n_cols, int32_t n_sel,
+                            const uint32_t* d_lo, const uint32_t* d_hi, int32_t level,
+                            int32_t* d_counts, void* stream);
+int iqw_radix_count_f32(const float* d_p, int64_t n_rows, int64_t n_cols, int32_t n_sel,
+                        const uint32_t* d_lo, const uint32_t* d_hi, int32_t level,
+                        int32_t* d_counts, int32_t* d_below, void* stream);
+int iqw_radix_descend(const int32_t* d_counts, int32_t n_sel, int64_t n_cols, int32_t level,
+                      int64_t* d_rank, uint32_t* d_prefix, uint32_t* d_lo, uint32_t* d_hi,
+                      void* stream);
+int iqw_order_stats_finish_f32(const uint32_t* d_keys, int32_t n_sel, const int64_t* sel_rank,
+                               int64_t n_rows_total, int64_t n_cols, const iqw_stat* stats,
+                               int32_t n_stats, int32_t to_dB, float eps, float* d_out, void* stream);
 
 /* Tuning aid: bytes of scratch iqw_stft_workspace_bytes asks for (nfft > 8192); frames are
  * processed in chunks of that size. */

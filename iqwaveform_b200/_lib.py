@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libiqw_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # statuses / enums mirrored from include/iqw_b200.h
 IQW_OK = 0
@@ -23,7 +23,7 @@ IQW_ERR_CUDA = -3
 IQW_ERR_WORKSPACE = -4
 
 STFT_COMPLEX, STFT_POWER, STFT_DB = 0, 1, 2
-STAT_QUANTILE, STAT_MEAN, STAT_MAX, STAT_MIN, STAT_MEDIAN = 0, 1, 2, 3, 4
+STAT_QUANTILE, STAT_MEAN, STAT_MAX, STAT_MIN, STAT_MEDIAN, STAT_ORDER = 0, 1, 2, 3, 4, 5
 EW_POWTODB, EW_DBTOPOW, EW_ENVTOPOW, EW_ENVTODB = 0, 1, 2, 3
 
 MAX_RANKS_PER_CALL = 8
@@ -56,6 +56,13 @@ SIGNATURES = {
     'iqw_envtopow_transposed_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     'iqw_elementwise_f32': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i32, _f32, _vp]),
     'iqw_elementwise_c64': (ctypes.c_int, [_i32, _vp, _vp, _i64, _f32, _vp]),
+    'iqw_bracket_collect_workspace_bytes': (_sz, [_i64, _i64]),
+    'iqw_bracket_collect_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'iqw_candidate_count_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
+    'iqw_radix_count_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    'iqw_radix_descend': (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'iqw_order_stats_finish_f32': (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i64), _i64, _i64,
+                                                  ctypes.POINTER(iqw_stat), _i32, _i32, _f32, _vp, _vp]),
     'iqw_debug_set_stft_scratch_cap': (ctypes.c_int, [_sz]),
     'iqw_debug_set_sample_margin': (ctypes.c_int, [ctypes.c_double, ctypes.c_int]),
     'iqw_debug_time_stats_counters': (ctypes.c_int, [_vp, _i64, ctypes.POINTER(ctypes.c_uint32)]),

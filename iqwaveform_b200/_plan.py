@@ -190,6 +190,8 @@ def distinct_ranks(reqs, n_rows: int) -> set:
     for r in reqs:
         if r.kind == _lib.STAT_QUANTILE:
             ranks.update((r.rank_lo, r.rank_hi))
+        elif r.kind == _lib.STAT_ORDER:
+            ranks.add(r.rank_lo)
         elif r.kind == _lib.STAT_MEDIAN:
             ranks.update(((n_rows - 1) // 2, n_rows // 2))
     return ranks

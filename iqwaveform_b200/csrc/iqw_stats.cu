@@ -1323,6 +1323,8 @@ __global__ void finalize_kernel(long long rows, long long cols, StatPlan st, int
             const float b = xf(w.r_key[col * kMaxRanks + st.ib[t]]);
             if (kind == IQW_STAT_MEDIAN) {
                 r = __fmul_rn(__fadd_rn(a, b), 0.5f);
+            } else if (kind == IQW_STAT_ORDER) {
+                r = a;      // no arithmetic: +-inf stay what they are (a lerp would give inf - inf)
             } else {
                 // numpy _lerp: a + (b-a)*g, or b - (b-a)*(1-g) where g >= 0.5; no fused ops
                 const float g = st.gamma[t];
@@ -1349,12 +1351,12 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
         st->kind[i] = s.kind;
         st->gamma[i] = s.gamma;
         st->ia[i] = st->ib[i] = 0;
-        if (s.kind < 0 || s.kind > IQW_STAT_MEDIAN)
+        if (s.kind < 0 || s.kind > IQW_STAT_ORDER)
             return fail(IQW_ERR_INVALID, "statistic %d: unknown kind %d", i, s.kind);
         if (s.kind == IQW_STAT_MEAN) *want_sum = true;
-        if (s.kind == IQW_STAT_QUANTILE || s.kind == IQW_STAT_MEDIAN) {
+        if (s.kind == IQW_STAT_QUANTILE || s.kind == IQW_STAT_MEDIAN || s.kind == IQW_STAT_ORDER) {
             const int64_t lo = s.kind == IQW_STAT_MEDIAN ? (rows - 1) / 2 : s.rank_lo;
-            const int64_t hi = s.kind == IQW_STAT_MEDIAN ? rows / 2 : s.rank_hi;
+            const int64_t hi = s.kind == IQW_STAT_MEDIAN ? rows / 2 : s.kind == IQW_STAT_ORDER ? s.rank_lo : s.rank_hi;
             if (lo < 0 || hi < lo || hi >= rows)
                 return fail(IQW_ERR_INVALID, "statistic %d: ranks (%lld, %lld) outside [0, %lld)", i,
                             (long long)lo, (long long)hi, (long long)rows);
@@ -1377,9 +1379,9 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
     for (int i = 0; i < nu; ++i) rp->rank[i] = (unsigned)ranks[i];
     for (int i = 0; i < n_stats; ++i) {
         const iqw_stat& s = stats[i];
-        if (s.kind != IQW_STAT_QUANTILE && s.kind != IQW_STAT_MEDIAN) continue;
+        if (s.kind != IQW_STAT_QUANTILE && s.kind != IQW_STAT_MEDIAN && s.kind != IQW_STAT_ORDER) continue;
         const int64_t lo = s.kind == IQW_STAT_MEDIAN ? (rows - 1) / 2 : s.rank_lo;
-        const int64_t hi = s.kind == IQW_STAT_MEDIAN ? rows / 2 : s.rank_hi;
+        const int64_t hi = s.kind == IQW_STAT_MEDIAN ? rows / 2 : s.kind == IQW_STAT_ORDER ? s.rank_lo : s.rank_hi;
         for (int k = 0; k < nu; ++k) {
             if (ranks[k] == lo) st->ia[i] = k;
             if (ranks[k] == hi) st->ib[i] = k;

@@ -190,9 +190,11 @@ def spectrogram(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, 
 
 
 def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25,
-                    out: torch.Tensor | None = None, counters: list | None = None) -> torch.Tensor:
+                    out: torch.Tensor | None = None, counters: list | None = None,
+                    requests: list | None = None) -> torch.Tensor:
     """statistics over axis 1 of a (C, T, nbins) float32 device tensor -> (C, nstat, nbins).
-    The device-side part of fourier.py:1311-1325."""
+    The device-side part of fourier.py:1311-1325.  `requests` (prebuilt iqw_stat records) replaces
+    `statistics` when the caller has done the rank arithmetic itself."""
     if p.dtype != torch.float32 or p.ndim != 3:
         raise ValueError('expected a (channels, frames, bins) float32 tensor')
     if not p.is_contiguous():
@@ -200,7 +202,7 @@ def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25
     C, T, nb = p.shape
     if T < 1:
         raise ValueError('cannot take statistics over zero frames')
-    reqs = _plan.stat_requests(list(statistics), T)
+    reqs = list(requests) if requests is not None else _plan.stat_requests(list(statistics), T)
     if out is None:
         out = torch.empty((C, len(reqs), nb), dtype=torch.float32, device=p.device)
     ws_bytes = _lib.lib.iqw_time_stats_workspace_bytes(C, T, nb, len(reqs))
@@ -224,12 +226,8 @@ def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25
     return out
 
 
-def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: float,
-                           fractional_overlap=0, fractional_window: float = 1, statistics,
-                           truncate=True, dB=True, axis=0):
-    """persistence spectrum: per-bin statistics over time of the (dB) power spectrogram.
-    Same arguments as the reference (fourier.py:1236-1327); returns (channels, nstat, nbins)
-    float32 for (channels, time) input with axis=1, (nstat, nbins) for 1-D input."""
+def _psd_frame_plan(fs, resolution, fractional_overlap, fractional_window):
+    """nfft, noverlap, nzero of a persistence spectrum and the reference's checks (fourier.py:1250-1262)"""
     if _plan.isroundmod(fs, resolution):
         nfft = round(fs / resolution)
         noverlap = round(fractional_overlap * nfft)
@@ -240,6 +238,16 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
     else:
         raise ValueError(
             '(1-fractional_window) * (sample_rate/frequency_resolution) must be a counting number')
+    return nfft, noverlap, nzero
+
+
+def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: float,
+                           fractional_overlap=0, fractional_window: float = 1, statistics,
+                           truncate=True, dB=True, axis=0):
+    """persistence spectrum: per-bin statistics over time of the (dB) power spectrogram.
+    Same arguments as the reference (fourier.py:1236-1327); returns (channels, nstat, nbins)
+    float32 for (channels, time) input with axis=1, (nstat, nbins) for 1-D input."""
+    nfft, noverlap, nzero = _psd_frame_plan(fs, resolution, fractional_overlap, fractional_window)
     statistics = list(statistics)
     _plan.stat_requests(statistics, 2)          # validates names before any device work
     domain = get_input_domain()

@@ -13,6 +13,7 @@ import torch.multiprocessing as mp
 from iqwaveform_b200 import distributed as D
 from oracle import iqw_oracle as orc
 from oracle.make_golden import synth
+from _shard_ops_numpy import NumpyShardOps, float_to_key
 
 
 def test_shard_planners_cover_everything_once():
@@ -85,21 +86,39 @@ def _worker(rank, world, port, out_dir):
                                            kind=kind, compute=lambda a, *p, **k: orc.iq_to_bin_power(a.numpy(), *p, **k))
             want = orc.iq_to_bin_power(x2, Ts, Tbin, kind=kind, truncate=True)
             assert np.array_equal(pw.numpy(), want)
-        # --- time-sharded persistence spectrum, reducible statistics (one all_reduce each) ---
-        N = 70001
-        x3 = synth(6, (N,))
-        pk = dict(fs=1e6, window='hann', resolution=1e6 / 256, fractional_overlap=0.5, dB=True)
-        stats = ['mean', 'max', 'min', 'peak']
-        fsh = D.frame_shard(N, 256, 128, world, rank)
-        got = D.persistence_spectrum_time_sharded(
-            torch.from_numpy(x3[fsh.sample0:fsh.sample1]), n_samples=N, statistics=stats,
-            compute=lambda a, **k: orc.persistence_spectrum(a.numpy(), **k), **pk)
-        want = orc.persistence_spectrum(x3, statistics=stats, axis=0, **pk)
-        assert np.array_equal(got.numpy()[1:], want[1:])                      # max / min / peak: exact
-        np.testing.assert_allclose(got.numpy()[0], want[0], atol=1e-3)        # mean of dB: fp32 summation order
-        with pytest.raises(NotImplementedError):
-            D.persistence_spectrum_time_sharded(torch.from_numpy(x3[fsh.sample0:fsh.sample1]), n_samples=N,
-                                                statistics=[0.5], **pk)
+        # --- time-sharded persistence spectrum: mean/max/min by one all_reduce each, quantiles and
+        #     median EXACT by the distributed radix select (4 all_reduce of digit counts) ---
+        for N, nfft, ov, bw in [(70001, 256, 0.5, float('inf')), (300, 256, 0.75, 0.5e6), (1000, 256, 0.75, 0.5e6)]:
+            x3 = synth(6, (N,))
+            pk = dict(fs=1e6, window='hann', resolution=1e6 / nfft, fractional_overlap=ov, dB=True, bandwidth=bw)
+            stats = ['mean', 0.1, 'max', 'min', 0.5, 'median', 'peak', 0.999, 1.0, 0.0]
+            fsh = D.frame_shard(N, nfft, round(ov * nfft), world, rank)
+            ops = NumpyShardOps()
+            got = D.persistence_spectrum_time_sharded(
+                torch.from_numpy(x3[fsh.sample0:fsh.sample1]), n_samples=N, statistics=stats, ops=ops, **pk).numpy()
+            assert ops.collected and (N < 70001 or not ops.overflowed)     # stationary capture: the bracketed path
+            want = orc.persistence_spectrum(x3, statistics=stats, axis=0, **pk)
+            assert got.shape == want.shape
+            assert np.array_equal(got[1:], want[1:])                      # order statistics, max, min: exact
+            np.testing.assert_allclose(got[0], want[0], atol=1e-3)        # mean of dB: fp32 summation order
+        # digital silence in most of the capture: heavy ties overflow the candidate store and the
+        # select falls back to counting over the whole local spectrogram; same exact result
+        N = 40000
+        x4 = synth(8, (N,))
+        x4[3000:33000] = 0
+        pk = dict(fs=1e6, window='hann', resolution=1e6 / 128, fractional_overlap=0.5, dB=True)
+        fsh = D.frame_shard(N, 128, 64, world, rank)
+        p4 = NumpyShardOps().power_spectrogram(x4[fsh.sample0:fsh.sample1], window='hann', nfft=128, noverlap=64,
+                                               nzero=0, bin_lo=0, bin_hi=128)
+        for sel, stored in [([fsh.n_frames // 2, fsh.n_frames // 2 + 1], False), ([fsh.n_frames - 3], None)]:
+            info = {}
+            keys = D.select_order_statistics(p4, sel, fsh.n_frames, ops=NumpyShardOps(), info=info)
+            assert stored is None or info['candidate_store'] is stored
+            full = orc.spectrogram(x4, fs=1e6, window='hann', nperseg=128, noverlap=64, axis=0, return_axis_arrays=False)
+            assert np.array_equal(keys.numpy().view(np.uint32), np.sort(float_to_key(full), axis=0)[sel])
+        with pytest.raises(ValueError):
+            D.persistence_spectrum_time_sharded(torch.from_numpy(x3[:5]), n_samples=N, statistics=[0.5],
+                                                ops=NumpyShardOps(), **pk)
         open(os.path.join(out_dir, f'ok{rank}'), 'w').close()
     finally:
         dist.destroy_process_group()

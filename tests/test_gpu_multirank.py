@@ -46,6 +46,14 @@ def _worker(rank, world, port, out_dir):
         bs = D.bin_shard(N, 1000, world, rank)
         pw = D.iq_to_bin_power_sharded(x1[bs.sample0:bs.sample1].contiguous(), 1e-6, 1e-3, n_samples=N, kind='peak')
         assert torch.equal(pw, iqw.iq_to_bin_power(x1, 1e-6, 1e-3, kind='peak', truncate=True))
+        # one capture split in time: exact quantiles through 4 NCCL all_reduce of digit counts
+        kw = dict(fs=1e6, window='hann', resolution=1e6 / 1024, fractional_overlap=0.5, dB=True,
+                  statistics=['mean', 0.1, 0.5, 'median', 0.999, 'max', 'min'])
+        sh = D.frame_shard(N, 1024, 512, world, rank)
+        got = D.persistence_spectrum_time_sharded(x1[sh.sample0:sh.sample1].contiguous(), n_samples=N, **kw)
+        want = iqw.persistence_spectrum(x1, axis=0, **kw)
+        assert torch.equal(got[1:], want[1:])
+        assert torch.allclose(got[0], want[0], atol=1e-3)
         open(os.path.join(out_dir, f'ok{rank}'), 'w').close()
     finally:
         dist.destroy_process_group()
