@@ -119,5 +119,36 @@ def main():
           x=x, **out)
 
 
+def make_inverse():
+    """istft / ola_filter fixtures; `python -m oracle.make_golden inverse`"""
+    ref = ref_shim.load()
+    if ref is None:
+        raise SystemExit('reference not present; golden fixtures can only be made in the build container')
+    fourier = ref.fourier
+    x = synth(15, (2, 8192))
+    for tag, kw, size in (
+        ('istft_hamming_256_128', dict(window='hamming', nperseg=256, noverlap=128), 8192),
+        ('istft_bh_1024_768', dict(window='blackmanharris', nperseg=1024, noverlap=768), None),
+        ('istft_rect_64_0', dict(window='rect', nperseg=64, noverlap=0), 8001),
+    ):
+        _, _, y = fourier.stft(x.copy(), fs=1e6, axis=1, truncate=False, **kw)
+        xr = fourier.istft(y.copy(), size, nfft=kw['nperseg'], noverlap=kw['noverlap'], axis=1)
+        _save(tag, dict(kw, fs=1e6, axis=1, size=size), y=y, x=np.ascontiguousarray(xr))
+    x = synth(16, (2, 16384))
+    for tag, kw in (
+        ('ola_hamming_512_all', dict(fs=1e6, nfft=512, window='hamming', passband=[-2e5, 2e5])),
+        # the reference's passband arithmetic only reacts to tiny values (oracle.ola_passband_bins)
+        ('ola_hamming_512_band', dict(fs=1e6, nfft=512, window='hamming',
+                                      passband=[-1.3647444248199463 - 2e-6, 1.3647444248199463 + 1e-6])),   # bins 129..316
+    ):
+        out = fourier.ola_filter(x.copy(), axis=1, **dict(kw, passband=tuple(kw['passband'])))
+        _save(tag, dict(kw, axis=1), x=x, out=np.ascontiguousarray(out))
+
+
 if __name__ == '__main__':
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'inverse':
+        make_inverse()
+    else:
+        main()
+        make_inverse()

@@ -84,3 +84,26 @@ def test_known_answers():
     np.testing.assert_allclose(p.max(axis=1), A * A, rtol=1e-5)
     # band edges: upper edge bin is dropped (fourier.py:1198)
     assert orc.freq_band_edges(256, 1 / 256, -64, 64) == (64, 192)
+
+
+ISTFT = ['istft_hamming_256_128', 'istft_bh_1024_768', 'istft_rect_64_0']
+OLA = ['ola_hamming_512_all', 'ola_hamming_512_band']
+
+
+@pytest.mark.parametrize('name', ISTFT)
+def test_istft_bitwise(name):
+    p, a = load_golden(name)
+    x = orc.istft(a['y'], p['size'], nfft=p['nperseg'], noverlap=p['noverlap'], axis=p['axis'])
+    assert x.dtype == np.complex64 and x.shape == a['x'].shape
+    assert np.array_equal(x.view(np.float32), a['x'].view(np.float32))
+
+
+@pytest.mark.parametrize('name', OLA)
+def test_ola_filter_bitwise(name):
+    p, a = load_golden(name)
+    p['passband'] = tuple(p['passband'])
+    out = orc.ola_filter(a['x'], **p)
+    assert out.dtype == np.complex64 and out.shape == a['out'].shape
+    assert np.array_equal(out.view(np.float32), a['out'].view(np.float32))
+    if name.endswith('band'):       # the mask really removed something
+        assert np.abs(out).mean() < 0.8 * np.abs(a['x']).mean()

@@ -128,3 +128,35 @@ def test_frequency_domain_persistence_matches_reference():
             got = orc.persistence_spectrum_from_stft(X.copy(), fs=1e6, bandwidth=bw, resolution=1e6 / 256,
                                                      fractional_overlap=0.5, statistics=stats, dB=dB, axis=1)
             assert got.shape == want.shape and np.array_equal(got, want), (dB, bw)
+
+
+@pytest.mark.parametrize('shape,axis', [((4096 * 3,), 0), ((3, 2048 * 5), 1), ((2, 3, 4096), 2)])
+@pytest.mark.parametrize('nfft,noverlap', [(256, 128), (256, 192), (64, 0), (128, 112), (1024, 512)])
+def test_istft(shape, axis, nfft, noverlap):
+    x = synth(9, shape)
+    _, _, y = ref.fourier.stft(x.copy(), fs=1e6, window='hamming', nperseg=nfft, noverlap=noverlap, truncate=False,
+                               axis=axis)
+    for size in (None, x.shape[axis], x.shape[axis] - 37):
+        a = ref.fourier.istft(y.copy(), size, nfft=nfft, noverlap=noverlap, axis=axis)
+        b = orc.istft(y.copy(), size, nfft=nfft, noverlap=noverlap, axis=axis)
+        assert a.shape == b.shape and np.array_equal(a.view(np.float32), b.view(np.float32))
+
+
+@pytest.mark.parametrize('shape,axis', [((8192,), 0), ((3, 4096), 1)])
+@pytest.mark.parametrize('passband', [(-2e5, 2e5), (-1.3647444248199463 - 2e-6, 1.3647444248199463 + 1e-6)])
+def test_ola_filter(shape, axis, passband):
+    x = synth(10, shape)
+    kw = dict(fs=1e6, nfft=512, window='hamming', passband=passband, axis=axis)
+    a = ref.fourier.ola_filter(x.copy(), **kw)
+    b = orc.ola_filter(x.copy(), **kw)
+    assert a.shape == b.shape and np.array_equal(a.view(np.float32), b.view(np.float32))
+
+
+def test_ola_filter_errors_match():
+    x = synth(10, (8192,))
+    for kw, exc in [(dict(window='hann'), TypeError), (dict(window='blackman'), ValueError),
+                    (dict(window='hamming', nfft=100), ValueError)]:
+        full = dict(dict(fs=1e6, nfft=512, window='hamming', passband=(-1e5, 1e5)), **kw)
+        for f in (ref.fourier.ola_filter, orc.ola_filter):
+            with pytest.raises(exc):
+                f(x.copy(), **full)
