@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libiqw_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # statuses / enums mirrored from include/iqw_b200.h
 IQW_OK = 0
@@ -56,6 +56,7 @@ SIGNATURES = {
     'iqw_envtopow_transposed_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     'iqw_elementwise_f32': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i32, _f32, _vp]),
     'iqw_elementwise_c64': (ctypes.c_int, [_i32, _vp, _vp, _i64, _f32, _vp]),
+    'iqw_istft_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _i64, _vp]),
     'iqw_bracket_collect_workspace_bytes': (_sz, [_i64, _i64]),
     'iqw_bracket_collect_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     'iqw_candidate_count_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),

@@ -120,6 +120,51 @@ def design_window(name_or_tuple, nwindow: int, nzero: int = 0, *, norm: bool = T
     return (sign * w).astype(np.float32)
 
 
+# ---------------------------------------------------------------------------------------------
+# overlap-add filter planning (host side of fourier.py:652-723, 1108-1181)
+# ---------------------------------------------------------------------------------------------
+_COLA = {'hamming': (2, 1 / 2), 'blackman': (3, 2 / 3), 'blackmanharris': (5, 4 / 5)}   # divisor, overlap
+
+
+def ola_overlap(array_size: int, window, nfft: int, nfft_out, extend: bool) -> tuple[int, int, float]:
+    """(nfft_out, noverlap, overlap fraction) of ola_filter with the reference's checks, in the
+    reference's order (fourier.py:656-691): window name, divisibility, whole hops in the input"""
+    nfft_out = nfft if nfft_out is None else nfft_out
+    if window in (None, 'rect'):
+        raise ValueError('unexpected matching error')       # what the reference raises for them
+    try:
+        divisor, frac = _COLA[window]
+    except (KeyError, TypeError):
+        raise TypeError('ola_filter argument "window" must be one of ("hamming", "blackman", or "blackmanharris")')
+    if nfft_out % divisor:
+        raise ValueError(f'{window!r} window COLA requires output nfft_out % {divisor} == 0')
+    noverlap = round(nfft_out * frac)
+    if array_size % noverlap and not extend:
+        raise ValueError(f'x.size ({array_size}) is not an integer multiple of noverlap ({noverlap})')
+    return nfft_out, noverlap, frac
+
+
+@functools.lru_cache()
+def enbw_symmetric_f32(window, n: int) -> np.float32:
+    """ENBW in bins of the SYMMETRIC window (fftbins=False), accumulated in float32 on the
+    float32 unit-power window, which is what ola_filter adds to its passband edges
+    (fourier.py:1146, 270-279)"""
+    from scipy import signal
+
+    w = signal.windows.get_window(window, n, fftbins=False)
+    w = (w / np.sqrt(np.mean(np.abs(w) ** 2))).astype(np.float32)
+    return len(w) * np.sum(w ** 2) / np.sum(w) ** 2
+
+
+def ola_mask_bins(nfft: int, fs: float, n_frames: int, lo, hi) -> tuple[int, int]:
+    """bins [ilo, ihi) that zero_stft_by_freq keeps (fourier.py:710-723).  The reference derives
+    the sample spacing it hands to the band-edge search from the FRAME count times the bin
+    spacing, so passbands in Hz select every bin; reproduced as is for drop-in behaviour."""
+    freqs = fftfreq(nfft, 1.0 / fs)
+    step = float(freqs[1] - freqs[0])
+    return freq_band_edges(nfft, n_frames * step, lo, hi)
+
+
 def window_key(window):
     """hashable form of a window argument"""
     if window is None:

@@ -21,6 +21,54 @@ struct StftArgs {
     long long groups_per_ch;   // ceil(n_frames / FPC)
 };
 
+// geometry of the in-CTA FFT (shared by the forward kernel, iqw_stft.cu, and the inverse one,
+// iqw_istft.cu)
+template <int LOG2N>
+struct StftCfg {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int E = plan_elems(LOG2N);
+    static constexpr int TPF = N / E;                           // threads per frame
+    static constexpr int THREADS = TPF >= 256 ? TPF : 256;
+    static constexpr int FPC = THREADS / TPF;                   // frames per CTA iteration
+    static constexpr int NP = plan_passes(LOG2N);
+    static constexpr int TW = plan_tw_size(LOG2N);
+    static constexpr int TW_ALLOC = (TW + 15) & ~15;
+    static constexpr int PADN = padded_size(N);
+    static constexpr int NBUF = NP > 1 ? 2 : 0;
+    static constexpr size_t SMEM = sizeof(float2) * ((size_t)TW_ALLOC + (size_t)NBUF * FPC * PADN);
+    // CTAs per SM we aim for (register budget = 65536 / (THREADS * MIN_BLOCKS))
+    static constexpr int MIN_BLOCKS = THREADS >= 512 ? 1 : 2;
+};
+
+template <int LOG2N, int P>
+struct PassLoop {
+    // runs passes P..NP-1; `par` selects the ping-pong buffer the NEXT exchange writes.  The
+    // twiddles of pass P+1 are fetched before the barrier that separates it from pass P.
+    static __device__ __forceinline__ void run(float2* v, float2* bufs, const float2* tw, const float2* t,
+                                               int ltid, int slot, int& par) {
+        using C = StftCfg<LOG2N>;
+        constexpr bool LAST = (P == C::NP - 1);
+        float2* wr = bufs + ((size_t)par * C::FPC + slot) * C::PADN;
+        const float2* rd = bufs + ((size_t)(par ^ 1) * C::FPC + slot) * C::PADN;
+        fft_pass<LOG2N, P>(v, rd, wr, t, ltid);
+        if constexpr (!LAST) {
+            constexpr int E = plan_elems(LOG2N);
+            float2 tn[E];
+            load_twiddles<LOG2N, P + 1>(tn, tw, ltid);
+            // only the threads of this frame slot exchange data: a named barrier per slot when a
+            // slot is made of whole warps, a warp barrier when it fits in one warp, the CTA barrier otherwise
+            if constexpr (C::TPF <= 32)
+                __syncwarp();                       // the slot lives inside one warp
+            else if constexpr (C::FPC > 1 && C::TPF % 32 == 0)
+                asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(C::TPF) : "memory");
+            else
+                __syncthreads();
+            par ^= 1;
+            PassLoop<LOG2N, P + 1>::run(v, bufs, tw, tn, ltid, slot, par);
+        }
+    }
+};
+
 // immutable per-(device, log2 n) twiddle table of the in-CTA FFT (built on first use)
 int get_twiddles(int log2n, cudaStream_t stream, const float2** out);
 

@@ -26,8 +26,8 @@ from . import _arrays, _lib, _plan
 from .util import Domain, get_input_domain
 from ._plan import INF
 
-__all__ = ['stft', 'spectrogram', 'power_spectral_density', 'persistence_spectrum', 'fftfreq',
-           'get_window', 'equivalent_noise_bandwidth']
+__all__ = ['stft', 'istft', 'ola_filter', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
+           'fftfreq', 'get_window', 'equivalent_noise_bandwidth']
 
 fftfreq = _plan.fftfreq
 
@@ -168,6 +168,94 @@ def stft(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, nzero: 
     ax = axis if axis >= 0 else axis + xd.ndim
     freqs, times = _plan.stft_axes(fs, int(nperseg), y.shape[ax], noverlap / nperseg)
     return freqs, times, y
+
+
+def _istft_device(y3: torch.Tensor, nfft: int, noverlap: int, bin_lo: int = 0, bin_hi=None,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """(C, T, nfft) complex64 STFT on the device -> (C, T*hop + noverlap) complex64 waveform: band
+    mask, inverse FFT, (-1)^n and overlap-add in one kernel (csrc/iqw_istft.cu)"""
+    if y3.dtype != torch.complex64:
+        raise NotImplementedError(f'only complex64 STFTs are built (got {y3.dtype})')
+    C, T, nb = y3.shape
+    if nb != nfft:
+        raise ValueError(f'the axis after the frame axis must hold nfft = {nfft} bins, got {nb}')
+    hop = nfft - noverlap
+    if hop < 1 or noverlap < 0:
+        raise ValueError('need 0 <= noverlap < nfft')
+    if nfft % hop:
+        raise NotImplementedError(
+            'istft: nfft must be a multiple of the hop (the reference adds groups of nfft // hop '
+            'frames, fourier.py:628-647, which is not an overlap-add otherwise)')
+    if T < 1 or C < 1:
+        raise IndexError('cannot invert an STFT without frames')
+    if not y3.is_contiguous():
+        y3 = y3.contiguous()
+    n_out = T * hop + noverlap
+    if out is None:
+        out = torch.empty((C, n_out), dtype=torch.complex64, device=y3.device)
+    elif out.shape != (C, n_out) or out.dtype != torch.complex64 or not out.is_contiguous() or out.device != y3.device:
+        raise ValueError(f'out must be a contiguous complex64 device tensor of shape {(C, n_out)}')
+    _lib.check(_lib.lib.iqw_istft_c64(
+        ctypes.c_void_p(y3.data_ptr()), C, T, T * nfft, nfft, hop, bin_lo, nfft if bin_hi is None else bin_hi,
+        ctypes.c_void_p(out.data_ptr()), n_out, _stream_ptr(y3.device)))
+    return out
+
+
+def _trim_center(x: torch.Tensor, size, axis: int) -> torch.Tensor:
+    """fourier.py:1098-1103: drop trim//2 samples at the start and the rest of the excess at the end"""
+    if size is None:
+        return x
+    trim = x.shape[axis] - size
+    if trim <= 0:
+        return x
+    return x.narrow(axis, trim // 2, size)
+
+
+def istft(y, size=None, *, nfft: int, noverlap: int, out=None, overwrite_x=False, axis: int = 0):
+    """reconstruct a waveform from its STFT; same arguments as the reference (fourier.py:1060-1105).
+    ``axis`` is the frame axis of ``y`` and ``axis + 1`` its (fft-shifted) bin axis; the result has the
+    waveform axis in their place.  Like the reference this is the plain overlap-add of the inverse
+    transformed frames -- it inverts ``stft(..., norm=None)``, whose window carries the COLA scale."""
+    yd, res = _arrays.to_device(y)
+    if axis < 0:
+        axis += yd.ndim
+    if not 0 <= axis < yd.ndim - 1:
+        raise ValueError('axis must address the frame axis, with the bin axis right after it')
+    lead, trail = tuple(yd.shape[:axis]), tuple(yd.shape[axis + 2:])
+    T, nb = yd.shape[axis], yd.shape[axis + 1]
+    if trail:       # frames and bins last
+        yd = yd.movedim((axis, axis + 1), (-2, -1))
+    y3 = yd.reshape(-1, T, nb)
+    x = _istft_device(y3, int(nfft), int(noverlap),
+                      out=out if (out is not None and not trail and not lead) else None)
+    x = _arrays.restore_layout(x, lead, trail, 1)
+    return res.give_back(_trim_center(x, size, axis))
+
+
+def ola_filter(x, *, fs: float, nfft: int, window='hamming', passband, nfft_out: int | None = None,
+               frequency_shift=False, axis: int = 0, extend=False, out=None, overwrite_x=False):
+    """band-pass filter by STFT overlap-and-add; same arguments as the reference
+    (fourier.py:1108-1181): ``stft(norm=None, truncate=False)`` with a COLA window, the bins outside
+    the passband zeroed (folded into the inverse kernel as a read mask), ``istft`` trimmed to the
+    input size.  The resampling variants (``nfft_out != nfft``, ``frequency_shift``) are not built.
+    NOTE the reference's passband arithmetic (fourier.py:714-715) works on a frequency axis scaled by
+    the frame count, so passbands given in Hz keep every bin; this is reproduced, not repaired."""
+    xd, res = _arrays.to_device(x)
+    nfft = int(nfft)
+    nfft_out, noverlap, frac = _plan.ola_overlap(xd.numel(), window, nfft, nfft_out, bool(extend))
+    if nfft_out != nfft or frequency_shift:
+        raise NotImplementedError('ola_filter: resampling (nfft_out != nfft, frequency_shift) is not built')
+    enbw = _plan.enbw_symmetric_f32(window, nfft_out)
+    lo, hi = passband[0] + enbw, passband[1] - enbw         # TypeError for None, as in the reference
+    _host_checks(xd, axis, nfft, round(nfft * frac), False)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+    y = _stft_device(x2, window=window, nfft=nfft, noverlap=round(nfft * frac), nzero=0, norm=None,
+                     truncate=False, mode=_lib.STFT_COMPLEX)
+    ilo, ihi = _plan.ola_mask_bins(nfft, fs, y.shape[1], lo, hi)
+    xf = _istft_device(y, nfft_out, noverlap, bin_lo=ilo, bin_hi=ihi)
+    ax = axis if axis >= 0 else axis + xd.ndim
+    xf = _arrays.restore_layout(xf, lead, trail, 1)
+    return res.give_back(_trim_center(xf, round(xd.shape[ax] * nfft_out / nfft), ax))
 
 
 def spectrogram(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, nzero: int = 0,

@@ -40,3 +40,13 @@ def db_tol(ref_db, peak_power, eps=0.0):
     p = 10.0 ** (np.asarray(ref_db, dtype=np.float64) / 10.0)
     p = np.maximum(p, 1e-300)
     return DB_ATOL + DB_PER_REL * (POWER_RTOL + POWER_FLOOR * peak_power / p)
+
+
+WAVE_FLOOR = 4e-7
+
+
+def waveform_tol(ref_x):
+    """inverse STFT / overlap-add output: |dx| <= 0.5e-5*|x| + 4e-7*max_n|x| (two float32 inverse
+    FFTs differ by rounding noise proportional to the frame energy; 2..4 frames are summed)"""
+    mag = np.abs(ref_x)
+    return 0.5 * POWER_RTOL * mag + WAVE_FLOOR * np.max(mag, axis=-1, keepdims=True)
