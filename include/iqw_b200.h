@@ -168,6 +168,17 @@ int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t
                   int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, void* d_out,
                   int64_t out_channel_stride, void* stream);
 
+/* The whole of ola_filter (fourier.py:1108-1181 with nfft_out == nfft) in ONE kernel: overlapped
+ * frame gather * window -> FFT -> zero the bins outside [bin_lo, bin_hi) -> inverse FFT -> (-1)^n ->
+ * overlap-add.  The STFT is never written: 8 B read + 8 B written per sample.  d_x / d_window /
+ * nfft / hop / n_frames as for iqw_stft_c64 (the window carries (-1)^n, 1/nfft and the COLA
+ * scale); d_out as for iqw_istft_c64.  Same result as iqw_stft_c64 (complex) + iqw_istft_c64. */
+int iqw_ola_filter_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,
+                       const float* d_window, int32_t nfft, int64_t hop, int64_t n_frames,
+                       int32_t bin_lo, int32_t bin_hi, void* d_out, int64_t out_channel_stride,
+                       void* stream);
+
+
 /* ---------------------------------------------------------------------------------------------
  * Exact order statistics of a float32 matrix whose ROWS are spread over several GPUs (the
  * time-sharded persistence spectrum; no reference counterpart -- the reference calls np.quantile

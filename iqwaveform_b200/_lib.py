@@ -57,6 +57,7 @@ SIGNATURES = {
     'iqw_elementwise_f32': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i32, _f32, _vp]),
     'iqw_elementwise_c64': (ctypes.c_int, [_i32, _vp, _vp, _i64, _f32, _vp]),
     'iqw_istft_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _i64, _vp]),
+    'iqw_ola_filter_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     'iqw_bracket_collect_workspace_bytes': (_sz, [_i64, _i64]),
     'iqw_bracket_collect_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     'iqw_candidate_count_f32': (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),

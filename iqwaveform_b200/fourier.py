@@ -233,11 +233,14 @@ def istft(y, size=None, *, nfft: int, noverlap: int, out=None, overwrite_x=False
 
 
 def ola_filter(x, *, fs: float, nfft: int, window='hamming', passband, nfft_out: int | None = None,
-               frequency_shift=False, axis: int = 0, extend=False, out=None, overwrite_x=False):
+               frequency_shift=False, axis: int = 0, extend=False, out=None, overwrite_x=False,
+               fused: bool = True):
     """band-pass filter by STFT overlap-and-add; same arguments as the reference
     (fourier.py:1108-1181): ``stft(norm=None, truncate=False)`` with a COLA window, the bins outside
-    the passband zeroed (folded into the inverse kernel as a read mask), ``istft`` trimmed to the
-    input size.  The resampling variants (``nfft_out != nfft``, ``frequency_shift``) are not built.
+    the passband zeroed, ``istft`` trimmed to the input size -- run as ONE kernel that never writes
+    the STFT (``fused=False``, an additive argument, runs the stft and istft kernels one after the
+    other instead; same result).  The resampling variants (``nfft_out != nfft``,
+    ``frequency_shift``) are not built.
     NOTE the reference's passband arithmetic (fourier.py:714-715) works on a frequency axis scaled by
     the frame count, so passbands given in Hz keep every bin; this is reproduced, not repaired."""
     xd, res = _arrays.to_device(x)
@@ -247,12 +250,26 @@ def ola_filter(x, *, fs: float, nfft: int, window='hamming', passband, nfft_out:
         raise NotImplementedError('ola_filter: resampling (nfft_out != nfft, frequency_shift) is not built')
     enbw = _plan.enbw_symmetric_f32(window, nfft_out)
     lo, hi = passband[0] + enbw, passband[1] - enbw         # TypeError for None, as in the reference
-    _host_checks(xd, axis, nfft, round(nfft * frac), False)
+    _host_checks(xd, axis, nfft, noverlap, False)
     x2, lead, trail = _arrays.as_channels(xd, axis)
-    y = _stft_device(x2, window=window, nfft=nfft, noverlap=round(nfft * frac), nzero=0, norm=None,
-                     truncate=False, mode=_lib.STFT_COMPLEX)
-    ilo, ihi = _plan.ola_mask_bins(nfft, fs, y.shape[1], lo, hi)
-    xf = _istft_device(y, nfft_out, noverlap, bin_lo=ilo, bin_hi=ihi)
+    if x2.dtype != torch.complex64:
+        raise NotImplementedError(f'only complex64 waveforms are built (got {x2.dtype})')
+    C, N = x2.shape
+    hop = nfft - noverlap
+    T = _frame_count(N, nfft, noverlap, False)
+    if T < 1:
+        raise ValueError('the waveform is shorter than one frame')
+    ilo, ihi = _plan.ola_mask_bins(nfft, fs, T, lo, hi)
+    if fused:
+        w = _device_window(window, nfft, 0, None, hop, x2.device)
+        xf = torch.empty((C, T * hop + noverlap), dtype=torch.complex64, device=x2.device)
+        _lib.check(_lib.lib.iqw_ola_filter_c64(
+            ctypes.c_void_p(x2.data_ptr()), C, N, x2.stride(0) if C > 1 else N, ctypes.c_void_p(w.data_ptr()),
+            nfft, hop, T, ilo, ihi, ctypes.c_void_p(xf.data_ptr()), xf.shape[1], _stream_ptr(x2.device)))
+    else:
+        y = _stft_device(x2, window=window, nfft=nfft, noverlap=noverlap, nzero=0, norm=None,
+                         truncate=False, mode=_lib.STFT_COMPLEX)
+        xf = _istft_device(y, nfft_out, noverlap, bin_lo=ilo, bin_hi=ihi)
     ax = axis if axis >= 0 else axis + xd.ndim
     xf = _arrays.restore_layout(xf, lead, trail, 1)
     return res.give_back(_trim_center(xf, round(xd.shape[ax] * nfft_out / nfft), ax))

@@ -99,6 +99,22 @@ def test_ola_filter_matches_oracle(passband, shape, axis):
     _check(iqw.ola_filter(x.copy(), **kw), orc.ola_filter(x.copy(), **kw))
 
 
+@pytest.mark.parametrize('nfft', [16, 64, 256, 1024, 2048, 4096, 8192])
+def test_fused_ola_filter_equals_the_two_kernel_chain(nfft):
+    """one kernel (no STFT in memory) against stft -> masked istft: the same arithmetic, bit for bit"""
+    x = torch.from_numpy(synth(nfft, (3, nfft * 40))).cuda()
+    e = float(orc.enbw_symmetric('hamming', nfft))
+    for pb in [(-2e5, 2e5), (-e - 2e-6 * 512 / nfft, e + 1e-6 * 512 / nfft)]:
+        kw = dict(fs=1e6, nfft=nfft, window='hamming', passband=pb, axis=1)
+        a = iqw.ola_filter(x, **kw)
+        b = iqw.ola_filter(x, fused=False, **kw)
+        assert torch.equal(a, b)
+    # a long capture: many frame ranges per channel
+    x = torch.from_numpy(synth(1, (2, nfft * 3000 if nfft <= 256 else nfft * 300))).cuda()
+    kw = dict(fs=1e6, nfft=nfft, window='hamming', passband=(-1e5, 1e5), axis=1)
+    assert torch.equal(iqw.ola_filter(x, **kw), iqw.ola_filter(x, fused=False, **kw))
+
+
 def test_errors_follow_the_reference():
     x = synth(10, (8192,))
     kw = dict(fs=1e6, nfft=512, window='hamming', passband=(-1e5, 1e5))

@@ -92,6 +92,17 @@ def main():
             ms = timed(lambda: iqw.spectrogram(x, fs=1e8, window='hann', nperseg=nfft, noverlap=nov,
                                                return_axis_arrays=False))
             rows.append(row(f'configs[4] spectrogram nfft {nfft} overlap {ov:.2f}', n, ms, 8 + 4 * nfft / (nfft - nov)))
+    # inverse STFT and the overlap-add filter (hamming, 50 % overlap), same capture
+    for nfft in (256, 1024, 4096):
+        nov = nfft // 2
+        y = iqw.stft(x, fs=1e8, window='hamming', nperseg=nfft, noverlap=nov, truncate=False, return_axis_arrays=False)
+        ms = timed(lambda: iqw.istft(y, n, nfft=nfft, noverlap=nov))
+        rows.append(row(f'(f3) istft nfft {nfft} overlap 0.50', n, ms, 24))
+        del y
+        ms = timed(lambda: iqw.ola_filter(x, fs=1e8, nfft=nfft, window='hamming', passband=(-2e7, 2e7)))
+        rows.append(row(f'(f3) ola_filter nfft {nfft} hamming, one kernel', n, ms, 16))
+        ms = timed(lambda: iqw.ola_filter(x, fs=1e8, nfft=nfft, window='hamming', passband=(-2e7, 2e7), fused=False))
+        rows.append(row(f'(f3) ola_filter nfft {nfft} hamming, stft + istft kernels', n, ms, 48))
     if a.out:
         json.dump({'hbm_peak_GBps': PEAK, 'rows': rows}, open(a.out, 'w'), indent=1)
 

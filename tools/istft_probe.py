@@ -34,6 +34,9 @@ for nfft in nffts:
         print(f'istft nfft {nfft} R {R}: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s  {n * by / ms / 1e6:.0f} GB/s '
               f'({n * by / ms / 1e6 / PEAK:.2f} of the measured HBM peak, {by} B/sample)')
         del y
-    ms = timed(lambda: iqw.ola_filter(x, fs=1e6, nfft=nfft, window='hamming', passband=(-2e5, 2e5)))
-    print(f'ola_filter nfft {nfft} hamming: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s  '
+    ms = timed(lambda: iqw.ola_filter(x, fs=1e6, nfft=nfft, window='hamming', passband=(-2e5, 2e5), fused=False))
+    print(f'ola_filter nfft {nfft} hamming, stft + istft kernels: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s  '
           f'({n * 48 / ms / 1e6 / PEAK:.2f} of the HBM peak at 48 B/sample: 8 in + 16 stft out + 16 in + 8 out)')
+    ms = timed(lambda: iqw.ola_filter(x, fs=1e6, nfft=nfft, window='hamming', passband=(-2e5, 2e5)))
+    print(f'ola_filter nfft {nfft} hamming, one kernel: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s  '
+          f'({n * 16 / ms / 1e6 / PEAK:.2f} of the HBM peak at 16 B/sample: 8 in + 8 out)')
