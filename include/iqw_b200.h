@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IQW_ABI_VERSION 4
+#define IQW_ABI_VERSION 5
 
 typedef enum iqw_status {
     IQW_OK = 0,
@@ -178,6 +178,18 @@ int iqw_ola_filter_c64(const void* d_x, int64_t n_channels, int64_t n_samples, i
                        int32_t bin_lo, int32_t bin_hi, void* d_out, int64_t out_channel_stride,
                        void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 5: counts[row][i] = number of samples x of the row with searchsorted(edges, x, side) == i,
+ * i = 0 .. n_edges.  The device part of power_analysis.py:552-583
+ * (sample_ccdf: side 'left', then N - cumsum) and util.py:497-543 (histogram_last_axis: side
+ * 'right', columns 1 .. n_edges-1 are the histogram).
+ *
+ *   d_a       (n_rows, n_cols) float32, C-contiguous      d_edges  n_edges float64, ascending
+ *   d_counts  (n_rows, n_edges + 1) int64, zeroed by the call.  n_edges <= 4096
+ */
+int iqw_edge_counts_f32(const float* d_a, int64_t n_rows, int64_t n_cols, const double* d_edges,
+                        int32_t n_edges, int32_t side_right, int64_t* d_counts, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Exact order statistics of a float32 matrix whose ROWS are spread over several GPUs (the

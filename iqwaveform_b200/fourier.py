@@ -26,7 +26,7 @@ from . import _arrays, _lib, _plan
 from .util import Domain, get_input_domain
 from ._plan import INF
 
-__all__ = ['stft', 'istft', 'ola_filter', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
+__all__ = ['stft', 'istft', 'ola_filter', 'iq_to_stft_spectrogram', 'channelize_power', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
            'fftfreq', 'get_window', 'equivalent_noise_bandwidth']
 
 fftfreq = _plan.fftfreq
@@ -292,6 +292,96 @@ def spectrogram(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, 
     ax = axis if axis >= 0 else axis + xd.ndim
     freqs, times = _plan.stft_axes(fs, int(nperseg), p.shape[ax], noverlap / nperseg)
     return freqs, times, p
+
+
+def _python_slice(n: int, start: int, stop_from_end: int) -> tuple[int, int]:
+    """bounds of range(n)[start:-stop_from_end] -- including python's [a:-0] == [a:0] (empty)"""
+    lo, hi, _ = slice(start, -stop_from_end).indices(n)
+    return lo, max(hi, lo)
+
+
+def iq_to_stft_spectrogram(iq, window, nfft: int, Ts, overlap=True, analysis_bandwidth=None):
+    """power spectrogram of a 1-D capture as a pandas DataFrame (index: frame times, columns:
+    frequencies); same arguments as the reference (fourier.py:1421-1456).  The analysis-bandwidth
+    trim is done by the STFT kernel (only the kept bins are computed into memory)."""
+    import pandas as pd
+
+    shape = getattr(iq, 'shape', None)
+    if shape is None:
+        raise TypeError('unrecognized object type')
+    if len(shape) != 1:
+        raise ValueError('iq_to_stft_spectrogram takes a 1-D waveform (a DataFrame is 2-D)')
+    nfft = int(nfft)
+    noverlap = nfft // 2 if overlap else 0
+    _check_window_arg(window)
+    _host_checks(iq, 0, nfft, noverlap, True)
+    T = _frame_count(shape[0], nfft, noverlap, True)
+    freqs, times = _plan.stft_axes(1.0 / Ts, nfft, T, noverlap / nfft)
+    lo, hi = 0, nfft
+    if analysis_bandwidth is not None:
+        throwaway = nfft * (1 - analysis_bandwidth * Ts)
+        if T > 1 and np.abs(throwaway - np.rint(throwaway)) > 1e-6:
+            raise ValueError(f'analysis bandwidth yield integral number of samples, but got {throwaway}')
+        lo, hi = _python_slice(nfft, int(np.floor(throwaway / 2)), int(np.ceil(throwaway // 2)))
+    xd, _ = _arrays.to_device(iq)
+    if hi > lo:
+        p = _stft_device(xd.reshape(1, -1), window=window, nfft=nfft, noverlap=noverlap, nzero=0, norm='power',
+                         truncate=True, mode=_lib.STFT_POWER, bin_lo=lo, bin_hi=hi)[0]
+        values = _arrays.Residence('numpy').give_back(p)
+    else:
+        values = np.empty((T, 0), dtype=np.float32)
+    return pd.DataFrame(values, columns=freqs[lo:hi], index=times)
+
+
+def channelize_power(iq, Ts: float, fft_size_per_channel: int, *, analysis_bins_per_channel: int, window,
+                     fft_overlap_per_channel=0, channel_count: int = 1, axis=0):
+    """time series of the power in each of `channel_count` adjacent channels; the reference's
+    arguments and return values (fourier.py:1330-1418).  The reference itself raises TypeError at its
+    first statement (it forwards the window as ``w=``, which ``stft`` does not accept, fourier.py:1387-1390);
+    this is the function with the window passed as ``window=``, everything else as written there --
+    including ``X[:, s:-s]`` being EMPTY when no bins are skipped."""
+    if axis != 0:
+        raise NotImplementedError('sorry, only axis=0 implemented for now')
+    if analysis_bins_per_channel > fft_size_per_channel:
+        raise ValueError('the number of analysis bins cannot be greater than FFT size')
+    shape = getattr(iq, 'shape', None)
+    if shape is None:
+        raise TypeError('unrecognized object type')
+    if len(shape) != 1:
+        raise NotImplementedError('channelize_power is built for 1-D captures')
+    nfft = int(fft_size_per_channel * channel_count)
+    noverlap = int(fft_overlap_per_channel * channel_count)
+    _check_window_arg(window)
+    _host_checks(iq, 0, nfft, noverlap, True)
+    skip = channel_count * (fft_size_per_channel - analysis_bins_per_channel)
+    if skip % 2 == 1:
+        raise ValueError('must pass an even number of bins to skip')
+    T = _frame_count(shape[0], nfft, noverlap, True)
+    freqs, times = _plan.stft_axes(1.0 / Ts, nfft, T, noverlap / nfft)
+    lo, hi = _python_slice(nfft, skip // 2, skip // 2)
+    freqs = freqs[lo:hi]
+    xd, res = _arrays.to_device(iq)
+    nb = hi - lo
+    if channel_count != 1 and nb == 0:
+        raise IndexError('index 0 is out of bounds for axis 0 with size 0')     # freqs[0] of an empty band
+    if channel_count != 1 and nb % analysis_bins_per_channel:
+        raise ValueError(f'axis 0 size {nb} is not a factor of block size {analysis_bins_per_channel}')
+    group = nb if channel_count == 1 else analysis_bins_per_channel
+    n_groups = 1 if channel_count == 1 else (nb // group if group else 0)
+    power = torch.zeros((T, n_groups), dtype=torch.float32, device=xd.device)
+    if nb > 0 and T > 0:
+        X = _stft_device(xd.reshape(1, -1), window=window, nfft=nfft, noverlap=noverlap, nzero=0, norm='power',
+                         truncate=True, mode=_lib.STFT_COMPLEX, bin_lo=lo, bin_hi=hi)      # (1, T, nb)
+        # sum of |X|^2 over each group of bins: kernel 3 on the flattened (T*nb) band, mean * size
+        ws_bytes = _lib.lib.iqw_bin_power_workspace_bytes(1, group, T * n_groups)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xd.device)
+        _lib.check(_lib.lib.iqw_bin_power_c64(
+            ctypes.c_void_p(X.data_ptr()), 1, T * nb, group, T * n_groups, ctypes.c_void_p(power.data_ptr()), None,
+            None, ctypes.c_void_p(ws.data_ptr()), ws_bytes, _stream_ptr(xd.device)))
+        power *= float(group)
+    if channel_count == 1:
+        return times, res.give_back(power[:, 0])
+    return freqs[:analysis_bins_per_channel], times, res.give_back(power)
 
 
 def time_statistics(p: torch.Tensor, statistics, *, dB: bool, eps: float = 1e-25,

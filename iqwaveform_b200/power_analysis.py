@@ -14,7 +14,8 @@ from . import _arrays, _lib, _plan
 from .fourier import _stream_ptr, time_statistics
 from .util import Domain, get_input_domain
 
-__all__ = ['iq_to_bin_power', 'iq_to_cyclic_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean', 'dBlinsum']
+__all__ = ['iq_to_bin_power', 'iq_to_cyclic_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean', 'dBlinsum',
+           'sample_ccdf']
 
 _DIRECT = {'mean': 'mean', 'rms': 'mean', 'max': 'max', 'peak': 'max', 'min': 'min'}
 
@@ -242,3 +243,38 @@ def dBlinmean(x_dB, axis=None, overwrite_x=False):
 def dBlinsum(x_dB, axis=None, overwrite_x=False):
     """sum in linear power of values in dB, power_analysis.py:321-338"""
     return _dBlin(x_dB, axis, 'sum')
+
+
+def _edge_counts(a2: torch.Tensor, edges, side_right: bool) -> torch.Tensor:
+    """(rows, n) float32 on the device, ascending edges -> (rows, n_edges + 1) int64 counts of
+    searchsorted(edges, a, side) (csrc/iqw_histogram.cu)"""
+    if a2.dtype != torch.float32:
+        raise NotImplementedError(f'only float32 samples are built (got {a2.dtype})')
+    if not a2.is_contiguous():
+        a2 = a2.contiguous()
+    e = torch.as_tensor(edges)
+    if e.ndim != 1 or e.numel() < 1:
+        raise ValueError('edges must be a non-empty vector')
+    e = e.to(device=a2.device, dtype=torch.float64).contiguous()
+    counts = torch.empty((a2.shape[0], e.numel() + 1), dtype=torch.int64, device=a2.device)
+    _lib.check(_lib.lib.iqw_edge_counts_f32(
+        ctypes.c_void_p(a2.data_ptr()), a2.shape[0], a2.shape[1], ctypes.c_void_p(e.data_ptr()), e.numel(),
+        int(side_right), ctypes.c_void_p(counts.data_ptr()), _stream_ptr(a2.device)))
+    return counts
+
+
+def sample_ccdf(a, edges, density: bool = True):
+    """fraction (or number) of the samples of the vector `a` that exceed each edge; same arguments as
+    the reference (power_analysis.py:552-583): searchsorted(edges, a, 'left') -> bincount ->
+    ``a.size - cumsum``, int64 counts or float64 fractions"""
+    ad, res = _arrays.to_device(a)
+    if ad.ndim != 1:
+        raise ValueError('object too deep for desired array')      # numpy.bincount's message for non-1-D input
+    if ad.numel() == 0:
+        raise ValueError('sample_ccdf of an empty vector')
+    counts = _edge_counts(ad.reshape(1, -1), edges, side_right=False)[0]
+    ccdf = (ad.shape[0] - counts.cumsum(0))[:-1]
+    if density:
+        # a tensor divisor: torch turns division by a python scalar into a multiplication by 1/n
+        ccdf = ccdf.to(torch.float64) / torch.tensor(ad.shape[0], dtype=torch.float64, device=ccdf.device)
+    return res.give_back(ccdf)

@@ -145,10 +145,30 @@ def make_inverse():
         _save(tag, dict(kw, axis=1), x=x, out=np.ascontiguousarray(out))
 
 
+def make_consumers():
+    """sample_ccdf / histogram_last_axis fixtures; `python -m oracle.make_golden consumers`"""
+    ref = ref_shim.load()
+    if ref is None:
+        raise SystemExit('reference not present; golden fixtures can only be made in the build container')
+    x = synth(17, (30000,))
+    p = ref.power_analysis.envtopow(x)
+    edges = np.linspace(0.0, 30.0, 61)
+    _save('ccdf_power_61', dict(), p=p, edges=edges,
+          density=ref.power_analysis.sample_ccdf(p, edges, density=True),
+          counts=ref.power_analysis.sample_ccdf(p, edges, density=False))
+    pdb = ref.power_analysis.powtodB(p.reshape(6, 5000).copy())
+    h, e = ref.util.histogram_last_axis(pdb, 50, (-30.0, 20.0))
+    _save('hist_db_50', dict(bins=50, range=[-30.0, 20.0]), x=pdb, hist=h, edges=e)
+
+
 if __name__ == '__main__':
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'consumers':
+        make_consumers()
+        raise SystemExit
     if len(sys.argv) > 1 and sys.argv[1] == 'inverse':
         make_inverse()
     else:
         main()
         make_inverse()
+        make_consumers()

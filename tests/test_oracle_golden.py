@@ -107,3 +107,12 @@ def test_ola_filter_bitwise(name):
     assert np.array_equal(out.view(np.float32), a['out'].view(np.float32))
     if name.endswith('band'):       # the mask really removed something
         assert np.abs(out).mean() < 0.8 * np.abs(a['x']).mean()
+
+
+def test_ccdf_and_histogram_bitwise():
+    _, a = load_golden('ccdf_power_61')
+    assert np.array_equal(orc.sample_ccdf(a['p'], a['edges'], density=True), a['density'])
+    assert np.array_equal(orc.sample_ccdf(a['p'], a['edges'], density=False), a['counts'])
+    p, a = load_golden('hist_db_50')
+    h, e = orc.histogram_last_axis(a['x'], p['bins'], tuple(p['range']))
+    assert np.array_equal(h, a['hist']) and np.array_equal(e, a['edges'])

@@ -160,3 +160,46 @@ def test_ola_filter_errors_match():
         for f in (ref.fourier.ola_filter, orc.ola_filter):
             with pytest.raises(exc):
                 f(x.copy(), **full)
+
+
+def test_sample_ccdf_and_histogram_last_axis():
+    rng = np.random.default_rng(3)
+    p = (rng.standard_normal(100000) ** 2).astype(np.float32)
+    p[::97] = 1.0
+    for edges in (np.linspace(0, 4, 41), np.array([1.0]), np.array([0.5, 1.0, 1.0, 2.0], dtype=np.float32)):
+        for density in (True, False):
+            a, b = ref.power_analysis.sample_ccdf(p, edges, density=density), orc.sample_ccdf(p, edges, density=density)
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+    x = rng.standard_normal((3, 5, 4000)).astype(np.float32)
+    x[0, 0, :10] = 2.0
+    for bins, rg in ((40, (-2.0, 2.0)), (7, None), (np.array([-1.0, 0.0, 0.25, 3.0]), None)):
+        (h, e), (h2, e2) = ref.util.histogram_last_axis(x, bins, rg), orc.histogram_last_axis(x, bins, rg)
+        assert h.shape == h2.shape and np.array_equal(h, h2) and np.array_equal(e, e2)
+
+
+@pytest.mark.parametrize('overlap,bw', [(True, None), (True, 0.5e6), (False, 0.75e6), (True, 1e6)])
+def test_iq_to_stft_spectrogram(overlap, bw):
+    x = synth(12, (20000,))
+    a = ref.fourier.iq_to_stft_spectrogram(x.copy(), 'hann', 256, 1e-6, overlap=overlap, analysis_bandwidth=bw)
+    b = orc.iq_to_stft_spectrogram(x.copy(), 'hann', 256, 1e-6, overlap=overlap, analysis_bandwidth=bw)
+    assert a.shape == b.shape and np.array_equal(a.values, b.values)
+    assert np.array_equal(a.columns.values, b.columns.values) and np.array_equal(a.index.values, b.index.values)
+
+
+def test_channelize_power_is_the_reference_with_the_window_forwarded():
+    """the reference raises before doing anything (w= is not an argument of stft); the oracle is the
+    same statements with window=, checked against the reference's own building blocks"""
+    x = synth(13, (30000,))
+    with pytest.raises(TypeError):
+        ref.fourier.channelize_power(x, 1e-6, 64, analysis_bins_per_channel=48, window='hann', channel_count=4)
+    for cc, ov in [(4, 0), (4, 32), (1, 0)]:
+        f, t, X = ref.fourier.stft(x.copy(), fs=1e6, window='hann', nperseg=64 * cc, noverlap=ov * cc, norm='power', axis=0)
+        s = cc * 16 // 2
+        X, f = X[:, s:-s], f[s:-s]
+        got = orc.channelize_power(x.copy(), 1e-6, 64, analysis_bins_per_channel=48, window='hann', channel_count=cc,
+                                   fft_overlap_per_channel=ov)
+        if cc == 1:
+            assert np.array_equal(got[0], t) and np.array_equal(got[1], ref.power_analysis.envtopow(X).sum(axis=1))
+        else:
+            want = ref.power_analysis.envtopow(X.reshape(X.shape[0], cc, 48)).sum(axis=2)
+            assert np.array_equal(got[0], f[:48]) and np.array_equal(got[1], t) and np.array_equal(got[2], want)
