@@ -76,24 +76,35 @@ istft_kernel(const IstftArgs a) {
     for (int j = 0; j < (A > 0 ? A : 1); ++j) acc[j] = make_float2(0.f, 0.f);
     int par = 0;
 
-#pragma unroll 1
-    for (long long m = f0 - (R - 1); m < f0 + a.frames_per_stream; ++m) {
-        float2 v[E];
+    // software pipeline: the bins of the NEXT frame are loaded while the current one is transformed
+    float2 nx[E];
+    auto prefetch = [&](long long m) {
         if (m >= 0 && m < f1) {
             const float2* fr = src + m * (long long)N;
 #pragma unroll
             for (int q = 0; q < E / R0; ++q)
 #pragma unroll
-                for (int r = 0; r < R0; ++r) {
-                    const int k = (ltid + q * TPF) + r * (N / R0);
-                    float2 z = __ldcs(fr + q * TPF + r * (N / R0));
-                    if (MASK && (k < a.bin_lo || k >= a.bin_hi)) z = make_float2(0.f, 0.f);
-                    v[q * R0 + r] = make_float2(z.x, -z.y);
-                }
+                for (int r = 0; r < R0; ++r) nx[q * R0 + r] = __ldcs(fr + q * TPF + r * (N / R0));
         } else {
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = make_float2(0.f, 0.f);
+            for (int e = 0; e < E; ++e) nx[e] = make_float2(0.f, 0.f);
         }
+    };
+    prefetch(f0 - (R - 1));
+
+#pragma unroll 1
+    for (long long m = f0 - (R - 1); m < f0 + a.frames_per_stream; ++m) {
+        float2 v[E];
+#pragma unroll
+        for (int q = 0; q < E / R0; ++q)
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const int k = (ltid + q * TPF) + r * (N / R0);
+                float2 z = nx[q * R0 + r];
+                if (MASK && (k < a.bin_lo || k >= a.bin_hi)) z = make_float2(0.f, 0.f);
+                v[q * R0 + r] = make_float2(z.x, -z.y);
+            }
+        prefetch(m + 1);
 
         PassLoop<LOG2N, 0>::run(v, bufs, tw, nullptr, ltid, slot, par);
 
@@ -184,20 +195,28 @@ ola_kernel(const OlaArgs a) {
     for (int j = 0; j < (A > 0 ? A : 1); ++j) acc[j] = make_float2(0.f, 0.f);
     int par = 0;
 
-#pragma unroll 1
-    for (long long m = f0 - (R - 1); m < f0 + a.frames_per_stream; ++m) {
-        float2 v[E];
+    // software pipeline: the samples of the NEXT frame are loaded while the current one is processed
+    float2 nx[E];
+    auto prefetch = [&](long long m) {
         if (m >= 0 && m < f1) {
             const float2* fr = src + m * HOP;
 #pragma unroll
             for (int q = 0; q < E / R0; ++q)
 #pragma unroll
-                for (int r = 0; r < R0; ++r)
-                    v[q * R0 + r] = cscale(__ldg(fr + q * TPF + r * (N / R0)), w[q * R0 + r]);
+                for (int r = 0; r < R0; ++r) nx[q * R0 + r] = __ldg(fr + q * TPF + r * (N / R0));
         } else {
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = make_float2(0.f, 0.f);
+            for (int e = 0; e < E; ++e) nx[e] = make_float2(0.f, 0.f);
         }
+    };
+    prefetch(f0 - (R - 1));
+
+#pragma unroll 1
+    for (long long m = f0 - (R - 1); m < f0 + a.frames_per_stream; ++m) {
+        float2 v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cscale(nx[e], w[e]);
+        prefetch(m + 1);
         PassLoop<LOG2N, 0>::run(v, bufs, tw, nullptr, ltid, slot, par);
 
         // band mask, conjugate, and rename into the load order of the inverse transform
