@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IQW_ABI_VERSION 5
+#define IQW_ABI_VERSION 6
 
 typedef enum iqw_status {
     IQW_OK = 0,
@@ -148,25 +148,34 @@ int iqw_elementwise_f32(int32_t op, const float* d_in, float* d_out, int64_t n, 
 int iqw_elementwise_c64(int32_t op, const void* d_in, float* d_out, int64_t n, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Kernel 4: inverse STFT with overlap-add, optionally band-masked.
+ * Kernel 4: inverse STFT with overlap-add, optionally band-masked / zero-padded / filtered
+ * (istft, ola_filter, oaresample).
  * Replaces fourier.py:1060-1105 (istft: ifft + the (-1)^n 'rect' window) + fourier.py:584-649
  * (_unstack_stft_windows) and, with a bin range, fourier.py:710-723 (zero_stft_by_freq, the
  * filter step of ola_filter, fourier.py:1108-1181), in ONE pass over the frames.
  *
- *   d_y          (n_channels, n_frames, nfft) complex64 STFT in the fft-shifted bin order that
+ *   d_y          (n_channels, n_frames, y_bins) complex64 STFT in the fft-shifted bin order that
  *                iqw_stft_c64 produces; channel stride y_channel_stride elements
  *   nfft         power of two, 16 <= nfft <= 8192
  *   hop          nfft/hop must be 1, 2, 4, 8 or 16 (the reference's own summation is only an
  *                overlap-add when hop divides nfft)
- *   bin_lo,bin_hi  bins outside [bin_lo, bin_hi) are read as zero (0, nfft = no mask)
+ *   bin_lo,bin_hi  bins outside [bin_lo, bin_hi) are taken as zero (0, nfft = no mask)
+ *   y_bins       bins STORED per frame: nfft (whole frames; the band is a read mask -- ola_filter),
+ *                or bin_hi - bin_lo (only the band is stored and sits at bins [bin_lo, bin_hi) of a
+ *                longer frame: the zero padding of the upsampling oaresample, fourier.py:1694-1699)
+ *   d_bin_gain   NULL, or nfft complex64 gains that multiply the bins (the frequency-domain FIR of
+ *                stft_fir_lowpass, fourier.py:803-826)
+ *   scale        factor applied to every output sample after the overlap-add (oaresample's
+ *                x.size/size_in*scale, fourier.py:1723; 1 otherwise)
  *   d_out        (n_channels, n_frames*hop + nfft - hop) complex64, channel stride
  *                out_channel_stride elements: every sample is the plain sum of the frames that
  *                cover it (no division by the window overlap, like the reference); the caller
  *                trims it (`size` argument of the reference) by slicing
  */
 int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t y_channel_stride,
-                  int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, void* d_out,
-                  int64_t out_channel_stride, void* stream);
+                  int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
+                  const void* d_bin_gain, float scale, void* d_out, int64_t out_channel_stride,
+                  void* stream);
 
 /* The whole of ola_filter (fourier.py:1108-1181 with nfft_out == nfft) in ONE kernel: overlapped
  * frame gather * window -> FFT -> zero the bins outside [bin_lo, bin_hi) -> inverse FFT -> (-1)^n ->

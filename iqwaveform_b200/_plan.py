@@ -165,6 +165,33 @@ def ola_mask_bins(nfft: int, fs: float, n_frames: int, lo, hi) -> tuple[int, int
     return freq_band_edges(nfft, n_frames * step, lo, hi)
 
 
+def downsample_copy_range(nfft_in: int, nfft_out: int, edge_lo, edge_hi) -> tuple[int, int]:
+    """input bins kept when frames of nfft_in bins shrink to nfft_out (fourier.py:813-847): the
+    nfft_out bins around the centre of [edge_lo, edge_hi) (the whole spectrum when both are None)"""
+    edge_lo = 0 if edge_lo is None else edge_lo
+    edge_hi = nfft_in if edge_hi is None else edge_hi
+    width = min(edge_hi - edge_lo, nfft_out)
+    first = (edge_hi + edge_lo) // 2 - width // 2
+    return max(first, 0), min(first + width, nfft_in)
+
+
+@functools.lru_cache(32)
+def fir_lowpass_gain(size: int, sample_rate: float, cutoff: float, transition: float) -> np.ndarray:
+    """complex64 per-bin gain of stft_fir_lowpass (fourier.py:766-826, window='rect'): the FFT of the
+    firwin2 taps in the fft-shifted bin order of the STFT; designed on the host like the windows"""
+    from scipy import signal
+
+    if cutoff == float('inf'):
+        taps = np.ones(size, dtype=np.complex64)
+    else:
+        taps = np.array(signal.firwin2(size, [0, cutoff, cutoff + transition, sample_rate / 2], [1.0, 1, 0.0, 0.0],
+                                       window='rect', fs=sample_rate)).astype(np.complex64)
+    sign = np.ones(size, dtype=np.float32)
+    sign[1::2] = -1.0
+    sign = sign.astype(np.complex64)
+    return (np.fft.fft(taps * sign) * sign).astype(np.complex64)
+
+
 def window_key(window):
     """hashable form of a window argument"""
     if window is None:

@@ -29,13 +29,17 @@ struct IstftArgs {
     int n_channels;
     long long n_frames;
     int bin_lo, bin_hi;
+    long long y_row;          // bins stored per frame: N, or bin_hi - bin_lo when only the band is stored
+    int y_off;                // bin index of the first stored bin (0, or bin_lo)
+    const float2* gain;       // optional per-bin complex gain (frequency-domain FIR), or null
+    float scale;              // factor applied to every output sample after the overlap-add
     float2* out;
     long long out_ch_stride;
     const float2* twiddle;
     long long streams_per_ch, frames_per_stream;
 };
 
-template <int LOG2N, int LOG2R, bool MASK>
+template <int LOG2N, int LOG2R, bool MASK, bool GAIN>
 __global__ void __launch_bounds__(StftCfg<LOG2N>::THREADS, StftCfg<LOG2N>::MIN_BLOCKS)
 istft_kernel(const IstftArgs a) {
     using C = StftCfg<LOG2N>;
@@ -80,11 +84,17 @@ istft_kernel(const IstftArgs a) {
     float2 nx[E];
     auto prefetch = [&](long long m) {
         if (m >= 0 && m < f1) {
-            const float2* fr = src + m * (long long)N;
+            const float2* fr = src + m * a.y_row - a.y_off;
 #pragma unroll
             for (int q = 0; q < E / R0; ++q)
 #pragma unroll
-                for (int r = 0; r < R0; ++r) nx[q * R0 + r] = __ldcs(fr + q * TPF + r * (N / R0));
+                for (int r = 0; r < R0; ++r) {
+                    const int k = (ltid + q * TPF) + r * (N / R0);
+                    if (!MASK || (k >= a.bin_lo && k < a.bin_hi))
+                        nx[q * R0 + r] = __ldcs(fr + q * TPF + r * (N / R0));
+                    else
+                        nx[q * R0 + r] = make_float2(0.f, 0.f);      // outside the stored / kept band
+                }
         } else {
 #pragma unroll
             for (int e = 0; e < E; ++e) nx[e] = make_float2(0.f, 0.f);
@@ -99,9 +109,8 @@ istft_kernel(const IstftArgs a) {
         for (int q = 0; q < E / R0; ++q)
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
-                const int k = (ltid + q * TPF) + r * (N / R0);
                 float2 z = nx[q * R0 + r];
-                if (MASK && (k < a.bin_lo || k >= a.bin_hi)) z = make_float2(0.f, 0.f);
+                if (GAIN) z = cmul(z, __ldg(a.gain + (ltid + q * TPF) + r * (N / R0)));
                 v[q * R0 + r] = make_float2(z.x, -z.y);
             }
         prefetch(m + 1);
@@ -123,11 +132,12 @@ istft_kernel(const IstftArgs a) {
         for (int j = 0; j < A; ++j) s[j] = make_float2(acc[j].x + s[j].x, acc[j].y + s[j].y);
         if (m >= f0 && m < f1) {
             float2* o = dst + m * HOP;
+            const float g = a.scale;
 #pragma unroll
-            for (int j = 0; j < H; ++j) __stcs(o + j * TPF, s[j]);
+            for (int j = 0; j < H; ++j) __stcs(o + j * TPF, make_float2(s[j].x * g, s[j].y * g));
             if (m == a.n_frames - 1) {      // the tail of the last frame: noverlap more samples
 #pragma unroll
-                for (int j = 0; j < A; ++j) __stcs(o + (j + H) * TPF, s[j + H]);
+                for (int j = 0; j < A; ++j) __stcs(o + (j + H) * TPF, make_float2(s[j + H].x * g, s[j + H].y * g));
             }
         }
 #pragma unroll
@@ -300,10 +310,10 @@ static int launch_ola(const OlaArgs& a, int log2r, cudaStream_t s) {
     return fail(IQW_ERR_UNSUPPORTED, "ola: nfft/hop = %d: only 1, 2, 4, 8, 16 are built", 1 << log2r);
 }
 
-template <int LOG2N, int LOG2R, bool MASK>
+template <int LOG2N, int LOG2R, bool MASK, bool GAIN>
 static int launch_istft_r(IstftArgs a, cudaStream_t stream) {
     using C = StftCfg<LOG2N>;
-    auto kern = istft_kernel<LOG2N, LOG2R, MASK>;
+    auto kern = istft_kernel<LOG2N, LOG2R, MASK, GAIN>;
     IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     int sms = 0, per_sm = 0;
     if (int rc = device_sm_count(&sms)) return rc;
@@ -331,8 +341,9 @@ static int launch_istft_m(const IstftArgs& a, cudaStream_t s) {
         return fail(IQW_ERR_UNSUPPORTED, "istft: nfft/hop = %d is larger than %d for nfft = %d", 1 << LOG2R,
                     plan_elems(LOG2N), 1 << LOG2N);
     } else {
-        if (a.bin_lo == 0 && a.bin_hi == (1 << LOG2N)) return launch_istft_r<LOG2N, LOG2R, false>(a, s);
-        return launch_istft_r<LOG2N, LOG2R, true>(a, s);
+        const bool full = a.bin_lo == 0 && a.bin_hi == (1 << LOG2N);
+        if (a.gain) return full ? launch_istft_r<LOG2N, LOG2R, false, true>(a, s) : launch_istft_r<LOG2N, LOG2R, true, true>(a, s);
+        return full ? launch_istft_r<LOG2N, LOG2R, false, false>(a, s) : launch_istft_r<LOG2N, LOG2R, true, false>(a, s);
     }
 }
 
@@ -353,8 +364,9 @@ static int launch_istft(const IstftArgs& a, int log2r, cudaStream_t s) {
 using namespace iqw;
 
 extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t y_channel_stride,
-                             int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, void* d_out,
-                             int64_t out_channel_stride, void* stream) {
+                             int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
+                             const void* d_bin_gain, float scale, void* d_out, int64_t out_channel_stride,
+                             void* stream) {
     if (!d_y || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (nfft < 2 || (nfft & (nfft - 1)))
         return fail(IQW_ERR_UNSUPPORTED, "nfft=%d: only powers of two are built", nfft);
@@ -368,12 +380,17 @@ extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_fram
     while (((int64_t)1 << log2r) < nfft / hop) ++log2r;
     if (n_channels < 1 || n_frames < 1) return fail(IQW_ERR_INVALID, "istft: need at least one channel and one frame");
     if (bin_lo < 0 || bin_hi > nfft || bin_lo > bin_hi) return fail(IQW_ERR_INVALID, "istft: bad bin range");
-    if (y_channel_stride < n_frames * nfft || out_channel_stride < n_frames * hop + (nfft - hop))
+    if (y_bins != nfft && y_bins != bin_hi - bin_lo)
+        return fail(IQW_ERR_INVALID, "istft: y_bins must be nfft (whole frames stored) or bin_hi - bin_lo (band only)");
+    if (y_bins < 1) return fail(IQW_ERR_INVALID, "istft: empty band");
+    if (y_channel_stride < n_frames * y_bins || out_channel_stride < n_frames * hop + (nfft - hop))
         return fail(IQW_ERR_INVALID, "istft: channel stride smaller than a channel");
     cudaStream_t s = (cudaStream_t)stream;
     IstftArgs a;
     a.y = (const float2*)d_y; a.y_ch_stride = y_channel_stride; a.n_channels = (int)n_channels;
     a.n_frames = n_frames; a.bin_lo = bin_lo; a.bin_hi = bin_hi;
+    a.y_row = y_bins; a.y_off = y_bins == nfft ? 0 : bin_lo;
+    a.gain = (const float2*)d_bin_gain; a.scale = scale;
     a.out = (float2*)d_out; a.out_ch_stride = out_channel_stride;
     a.streams_per_ch = a.frames_per_stream = 0;
     if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;

@@ -26,7 +26,7 @@ from . import _arrays, _lib, _plan
 from .util import Domain, get_input_domain
 from ._plan import INF
 
-__all__ = ['stft', 'istft', 'ola_filter', 'iq_to_stft_spectrogram', 'channelize_power', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
+__all__ = ['stft', 'istft', 'ola_filter', 'oaresample', 'iq_to_stft_spectrogram', 'channelize_power', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
            'fftfreq', 'get_window', 'equivalent_noise_bandwidth']
 
 fftfreq = _plan.fftfreq
@@ -171,13 +171,16 @@ def stft(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, nzero: 
 
 
 def _istft_device(y3: torch.Tensor, nfft: int, noverlap: int, bin_lo: int = 0, bin_hi=None,
-                  out: torch.Tensor | None = None) -> torch.Tensor:
-    """(C, T, nfft) complex64 STFT on the device -> (C, T*hop + noverlap) complex64 waveform: band
-    mask, inverse FFT, (-1)^n and overlap-add in one kernel (csrc/iqw_istft.cu)"""
+                  out: torch.Tensor | None = None, gain: torch.Tensor | None = None, scale: float = 1.0) -> torch.Tensor:
+    """(C, T, bins) complex64 STFT on the device -> (C, T*hop + noverlap) complex64 waveform: band
+    mask / zero padding, optional per-bin gain, inverse FFT, (-1)^n, overlap-add and a final scale in
+    one kernel (csrc/iqw_istft.cu).  `bins` is nfft (whole frames; [bin_lo, bin_hi) is a read mask)
+    or bin_hi - bin_lo (the frames hold only that band of an nfft-bin spectrum)."""
     if y3.dtype != torch.complex64:
         raise NotImplementedError(f'only complex64 STFTs are built (got {y3.dtype})')
     C, T, nb = y3.shape
-    if nb != nfft:
+    bin_hi = nfft if bin_hi is None else bin_hi
+    if nb != nfft and nb != bin_hi - bin_lo:
         raise ValueError(f'the axis after the frame axis must hold nfft = {nfft} bins, got {nb}')
     hop = nfft - noverlap
     if hop < 1 or noverlap < 0:
@@ -195,8 +198,11 @@ def _istft_device(y3: torch.Tensor, nfft: int, noverlap: int, bin_lo: int = 0, b
         out = torch.empty((C, n_out), dtype=torch.complex64, device=y3.device)
     elif out.shape != (C, n_out) or out.dtype != torch.complex64 or not out.is_contiguous() or out.device != y3.device:
         raise ValueError(f'out must be a contiguous complex64 device tensor of shape {(C, n_out)}')
+    if gain is not None and (gain.shape != (nfft,) or gain.dtype != torch.complex64 or not gain.is_contiguous()):
+        raise ValueError('gain must be a contiguous complex64 vector of nfft bins')
     _lib.check(_lib.lib.iqw_istft_c64(
-        ctypes.c_void_p(y3.data_ptr()), C, T, T * nfft, nfft, hop, bin_lo, nfft if bin_hi is None else bin_hi,
+        ctypes.c_void_p(y3.data_ptr()), C, T, T * nb, nfft, hop, bin_lo, bin_hi, nb,
+        ctypes.c_void_p(gain.data_ptr()) if gain is not None else None, float(scale),
         ctypes.c_void_p(out.data_ptr()), n_out, _stream_ptr(y3.device)))
     return out
 
@@ -292,6 +298,56 @@ def spectrogram(x, *, fs: float, window, nperseg: int = 256, noverlap: int = 0, 
     ax = axis if axis >= 0 else axis + xd.ndim
     freqs, times = _plan.stft_axes(fs, int(nperseg), p.shape[ax], noverlap / nperseg)
     return freqs, times, p
+
+
+def oaresample(x, up, down, fs, *, window='hamming', overwrite_x=False, axis=1, frequency_shift=0,
+               filter_bandwidth=None, transition_bandwidth=250e3, scale: float = 1.0):
+    """resample by up/down through STFT overlap-and-add; same arguments as the reference
+    (fourier.py:1627-1725).  `down` and `up` are the frame lengths of the forward and the inverse
+    transform.  Two kernels: the STFT writes only the bins that survive (downsampling: the `up` bins
+    around the centre, or around `frequency_shift`), the inverse kernel zero-pads (upsampling),
+    applies the optional frequency-domain FIR low-pass and the final x.size/size_in*scale factor."""
+    xd, res = _arrays.to_device(x)
+    nfft, nfft_in_out = int(down), int(up)
+    nfft_out, noverlap, frac = _plan.ola_overlap(xd.numel(), window, nfft, nfft_in_out, True)
+    if frequency_shift == 0:
+        edge_lo = edge_hi = None
+    elif down < up:
+        raise ValueError('frequency_shift is only supported when downsampling')
+    elif _plan.isroundmod(frequency_shift, fs / nfft):
+        shift = round(frequency_shift / (fs / nfft))
+        edge_lo = nfft // 2 - nfft_out // 2 + shift
+        edge_hi = edge_lo + nfft_out
+        if edge_lo < 0:
+            raise ValueError('frequency_shift is too small')
+        if edge_hi > nfft:
+            raise ValueError('frequency_shift is too large')
+    else:
+        raise ValueError('frequency_shift must be a multiple of fs/up')
+    nov_in = round(nfft * frac)
+    _host_checks(xd, axis, nfft, nov_in, False)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+    if nfft_out < nfft:         # downsample: only the kept bins are computed into memory
+        lo, hi = _plan.downsample_copy_range(nfft, nfft_out, edge_lo, edge_hi)
+        y = _stft_device(x2, window=window, nfft=nfft, noverlap=nov_in, nzero=0, norm=None, truncate=False,
+                         mode=_lib.STFT_COMPLEX, bin_lo=lo, bin_hi=hi)
+        place_lo, place_hi = 0, hi - lo
+        if place_hi != nfft_out:
+            raise NotImplementedError('oaresample: a passband narrower than the output frame is not built')
+    else:                       # upsample (or equal): the input spectrum sits in the middle of the output frame
+        y = _stft_device(x2, window=window, nfft=nfft, noverlap=nov_in, nzero=0, norm=None, truncate=False,
+                         mode=_lib.STFT_COMPLEX)
+        place_lo = (nfft_out - nfft) // 2
+        place_hi = place_lo + nfft
+    gain = None
+    if filter_bandwidth is not None and np.isfinite(filter_bandwidth):
+        g = _plan.fir_lowpass_gain(nfft_out, float(fs * up / down), float(filter_bandwidth / 2), float(transition_bandwidth))
+        gain = torch.from_numpy(g).to(x2.device)
+    n_out = y.shape[1] * (nfft_out - noverlap) + noverlap
+    factor = (x2.shape[0] * n_out) / xd.numel() * scale
+    xr = _istft_device(y, nfft_out, noverlap, bin_lo=place_lo, bin_hi=place_hi, gain=gain,
+                       scale=float(np.float32(factor)))
+    return res.give_back(_arrays.restore_layout(xr, lead, trail, 1))
 
 
 def _python_slice(n: int, start: int, stop_from_end: int) -> tuple[int, int]:

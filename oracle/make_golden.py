@@ -145,6 +145,21 @@ def make_inverse():
         _save(tag, dict(kw, axis=1), x=x, out=np.ascontiguousarray(out))
 
 
+def make_resample():
+    """oaresample fixtures; `python -m oracle.make_golden resample`"""
+    ref = ref_shim.load()
+    if ref is None:
+        raise SystemExit('reference not present; golden fixtures can only be made in the build container')
+    x = synth(18, (2, 8192))
+    for tag, kw in (
+        ('oares_down_1024_512', dict(up=512, down=1024)),
+        ('oares_up_512_1024_fir', dict(up=1024, down=512, filter_bandwidth=0.4e6, transition_bandwidth=100e3, scale=0.5)),
+        ('oares_shift_1024_256', dict(up=256, down=1024, frequency_shift=1e6 / 1024 * 100)),
+    ):
+        out = ref.fourier.oaresample(x.copy(), fs=1e6, axis=1, window='hamming', **kw)
+        _save(tag, dict(kw, fs=1e6, axis=1, window='hamming'), x=x, out=np.ascontiguousarray(out))
+
+
 def make_consumers():
     """sample_ccdf / histogram_last_axis fixtures; `python -m oracle.make_golden consumers`"""
     ref = ref_shim.load()
@@ -163,6 +178,9 @@ def make_consumers():
 
 if __name__ == '__main__':
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'resample':
+        make_resample()
+        raise SystemExit
     if len(sys.argv) > 1 and sys.argv[1] == 'consumers':
         make_consumers()
         raise SystemExit
@@ -171,4 +189,5 @@ if __name__ == '__main__':
     else:
         main()
         make_inverse()
+        make_resample()
         make_consumers()

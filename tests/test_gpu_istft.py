@@ -130,3 +130,44 @@ def test_errors_follow_the_reference():
         iqw.istft(y, nfft=128, noverlap=64)           # bin axis is not nfft long
     with pytest.raises(NotImplementedError):
         iqw.istft(np.zeros((4, 256), np.complex128), nfft=256, noverlap=128)
+
+
+@pytest.mark.parametrize('name', ['oares_down_1024_512', 'oares_up_512_1024_fir', 'oares_shift_1024_256'])
+def test_oaresample_golden(name):
+    p, a = load_golden(name)
+    _check(iqw.oaresample(a['x'], **p), a['out'])
+
+
+@pytest.mark.parametrize('shape,axis', [((2, 16384), 1), ((16384,), 0), ((32768, 2), 0)])
+@pytest.mark.parametrize('kw', [dict(up=512, down=1024), dict(up=1024, down=512), dict(up=1024, down=1024),
+                                dict(up=256, down=1024, frequency_shift=1e6 / 1024 * 100),
+                                dict(up=512, down=1024, filter_bandwidth=0.3e6, transition_bandwidth=50e3),
+                                dict(up=2048, down=1024, filter_bandwidth=0.6e6, scale=0.5),
+                                dict(up=8192, down=64), dict(up=32, down=4096)])
+def test_oaresample_matches_oracle(shape, axis, kw):
+    x = synth(14, shape[:axis] + shape[axis + 1:] + (shape[axis],))
+    want = orc.oaresample(x.copy(), fs=1e6, axis=x.ndim - 1, window='hamming', **kw)
+    got = iqw.oaresample(np.moveaxis(x, -1, axis).copy(), fs=1e6, axis=axis, window='hamming', **kw)
+    _check(np.moveaxis(got, axis, -1), want)
+
+
+def test_oaresample_errors_and_device_path():
+    x = synth(14, (2, 16384))
+    for bad, exc in [(dict(up=768, down=1024), NotImplementedError), (dict(up=1024, down=512, frequency_shift=1e3), ValueError),
+                     (dict(up=512, down=1024, frequency_shift=123.0), ValueError),
+                     (dict(up=256, down=1024, frequency_shift=0.45e6), ValueError), (dict(up=511, down=1024), ValueError)]:
+        with pytest.raises(exc):
+            iqw.oaresample(x, fs=1e6, axis=1, window='hamming', **bad)
+    with pytest.raises(TypeError):
+        iqw.oaresample(x, 512, 1024, 1e6, window='hann')
+    xd = torch.from_numpy(x).cuda()
+    a = iqw.oaresample(xd, 512, 1024, 1e6)
+    assert a.is_cuda and a.shape == (2, 8192)
+    # sanity, not parity: a 2:1 decimation keeps a slow tone (the cropped-spectrum overlap-add is only
+    # approximately shift-invariant, hence the per-cent level bound)
+    n = np.arange(1 << 16)
+    tone = np.exp(2j * np.pi * 0.01 * n).astype(np.complex64)
+    d = iqw.oaresample(tone, 512, 1024, 1e6, axis=0)
+    assert d.shape == (1 << 15,)
+    want = np.exp(2j * np.pi * 0.02 * np.arange(1 << 15))
+    assert np.max(np.abs(d[2048:-2048] - want[2048:-2048])) < 5e-2

@@ -116,3 +116,11 @@ def test_ccdf_and_histogram_bitwise():
     p, a = load_golden('hist_db_50')
     h, e = orc.histogram_last_axis(a['x'], p['bins'], tuple(p['range']))
     assert np.array_equal(h, a['hist']) and np.array_equal(e, a['edges'])
+
+
+@pytest.mark.parametrize('name', ['oares_down_1024_512', 'oares_up_512_1024_fir', 'oares_shift_1024_256'])
+def test_oaresample_bitwise(name):
+    p, a = load_golden(name)
+    out = orc.oaresample(a['x'], **p)
+    assert out.dtype == np.complex64 and out.shape == a['out'].shape
+    assert np.array_equal(out.view(np.float32), a['out'].view(np.float32))

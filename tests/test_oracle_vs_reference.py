@@ -203,3 +203,17 @@ def test_channelize_power_is_the_reference_with_the_window_forwarded():
         else:
             want = ref.power_analysis.envtopow(X.reshape(X.shape[0], cc, 48)).sum(axis=2)
             assert np.array_equal(got[0], f[:48]) and np.array_equal(got[1], t) and np.array_equal(got[2], want)
+
+
+@pytest.mark.parametrize('shape,axis', [((2, 16384), 1), ((16384,), 0)])
+@pytest.mark.parametrize('kw', [dict(up=512, down=1024), dict(up=1024, down=512), dict(up=1024, down=1024),
+                                dict(up=256, down=1024, frequency_shift=1e6 / 1024 * 100),
+                                dict(up=512, down=1024, filter_bandwidth=0.3e6, transition_bandwidth=50e3),
+                                dict(up=2048, down=1024, filter_bandwidth=0.6e6, scale=0.5),
+                                dict(up=768, down=1024)])
+def test_oaresample(shape, axis, kw):
+    x = synth(14, shape)
+    a = ref.fourier.oaresample(x.copy(), fs=1e6, axis=axis, window='hamming', **kw)
+    b = orc.oaresample(x.copy(), fs=1e6, axis=axis, window='hamming', **kw)
+    assert a.shape == b.shape and a.dtype == b.dtype
+    assert np.array_equal(a.view(np.float32), b.view(np.float32))

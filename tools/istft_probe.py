@@ -40,3 +40,9 @@ for nfft in nffts:
     ms = timed(lambda: iqw.ola_filter(x, fs=1e6, nfft=nfft, window='hamming', passband=(-2e5, 2e5)))
     print(f'ola_filter nfft {nfft} hamming, one kernel: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s  '
           f'({n * 16 / ms / 1e6 / PEAK:.2f} of the HBM peak at 16 B/sample: 8 in + 8 out)')
+
+for up, down in ((512, 1024), (2048, 1024), (1024, 4096)):
+    ms = timed(lambda: iqw.oaresample(x, up, down, 1e6, axis=0))
+    print(f'oaresample down={down} up={up}: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s in')
+ms = timed(lambda: iqw.oaresample(x, 512, 1024, 1e6, axis=0, filter_bandwidth=0.3e6, transition_bandwidth=50e3))
+print(f'oaresample down=1024 up=512 with the FIR low-pass: {ms:.3f} ms  {n / ms / 1e6:.1f} GS/s in')
