@@ -208,8 +208,11 @@ def run_b200(args):
         raise SystemExit('bench.py needs a GPU (the product path has no CPU fallback)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_cpus = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # one process per GPU: keep each rank's pinned host buffer on the socket its GPU hangs off
+        numa_cpus = iqw.distributed.bind_to_gpu_numa_node(local)
         dist.init_process_group('nccl', device_id=dev)
     n = args.samples
     warmup = max(args.warmup, 3)
@@ -275,7 +278,8 @@ def run_b200(args):
                'h2d_bytes_per_step': world * n * 8,
                'd2h_bytes_per_step': world * res.numel() * 4,
                'ms_per_step': dt / args.steps * 1e3,
-               'api': 'iqwaveform_b200.persistence_spectrum(pinned CPU torch tensor) -> CPU tensor'}
+               'api': 'iqwaveform_b200.persistence_spectrum(pinned CPU torch tensor) -> CPU tensor',
+               'host_cpus_rank0': numa_cpus}
         del host
 
     if rank != 0:

@@ -24,7 +24,8 @@ import torch
 import torch.distributed as dist
 
 __all__ = ['channel_shard', 'frame_shard', 'bin_shard', 'gather_rows', 'persistence_spectrum_sharded',
-           'persistence_spectrum_time_sharded', 'select_order_statistics', 'CudaShardOps', 'ThreadGroup', 'spectrogram_time_sharded', 'iq_to_bin_power_sharded']
+           'persistence_spectrum_time_sharded', 'select_order_statistics', 'CudaShardOps', 'ThreadGroup',
+           'bind_to_gpu_numa_node', 'spectrogram_time_sharded', 'iq_to_bin_power_sharded']
 
 
 def _split(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -104,6 +105,35 @@ def gather_rows(local: torch.Tensor, sizes: list[int] | None = None, axis: int =
     dist.all_gather(recv, send, group=group)
     out = torch.cat([r[:n] for r, n in zip(recv, sizes)], dim=0)
     return out.movedim(0, axis)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> str | None:
+    """pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned
+    host buffers it allocates afterwards (first touch) and its copy threads sit next to that GPU's
+    PCIe root: with one process per GPU, host->device copies of all ranks otherwise share one
+    socket's memory and the inter-socket link.  Returns the cpu list it bound to, or None when the
+    topology is not visible (no sysfs entry, single node, restricted cpuset) -- never raises."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
 
 
 def _world(group=None) -> tuple[int, int]:
