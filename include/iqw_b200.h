@@ -278,11 +278,14 @@ int iqw_debug_set_sample_margin(double sigmas, int extra_ranks);
 int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out16);
 
 /* ---------------------------------------------------------------------------------------------
- * Measurement aid (no reference counterpart): when enabled, every kernel launch of the library is
- * bracketed by CUDA events on the launching stream.  iqw_profile_report writes one text line per
- * kernel name, "<name> <launches> <total_ms>\n"; call it after synchronising the stream(s).
+ * Measurement aid (no reference counterpart): kernel launches of the library are bracketed by CUDA
+ * events on the launching stream.  level 0: off.  level 1: the heavy kernels one by one, and each
+ * train of small follow-up kernels (the fallback chain of iqw_time_stats_f32) as ONE scope, so that
+ * a timed region carries ~12 events per persistence-spectrum step instead of ~46 (which cost 2 % of
+ * it).  level 2: every launch.  iqw_profile_report writes one text line per scope name,
+ * "<name> <launches covered> <total_ms>\n"; call it after synchronising the stream(s).
  */
-int iqw_profile_enable(int on);
+int iqw_profile_enable(int level);
 int iqw_profile_reset(void);
 int iqw_profile_report(char* buf, size_t capacity);
 

@@ -114,9 +114,11 @@ def check(status: int) -> None:
     raise IQWError(f'iqw status {status}: {msg}')
 
 
-def profile(on: bool) -> None:
+def profile(on: bool, fine: bool = False) -> None:
+    """kernel timing by CUDA events on the launching stream: the heavy kernels one by one and the
+    trains of small follow-up kernels as one scope each; `fine=True` times every launch"""
     lib.iqw_profile_reset()
-    lib.iqw_profile_enable(int(on))
+    lib.iqw_profile_enable((2 if fine else 1) if on else 0)
 
 
 def profile_report() -> dict:

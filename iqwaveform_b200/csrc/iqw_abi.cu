@@ -28,15 +28,15 @@ int device_sm_count(int* sms) {
     return IQW_OK;
 }
 
-static std::atomic<bool> g_prof_on{false};
+static std::atomic<int> g_prof_level{0};
 static std::mutex g_prof_mutex;
-struct ProfRec { const char* name; cudaEvent_t a, b; };
+struct ProfRec { const char* name; int launches; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 
-bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
-void profile_push(const char* name, cudaEvent_t a, cudaEvent_t b) {
+int profile_level() { return g_prof_level.load(std::memory_order_relaxed); }
+void profile_push(const char* name, int launches, cudaEvent_t a, cudaEvent_t b) {
     std::lock_guard<std::mutex> lock(g_prof_mutex);
-    g_prof.push_back({name, a, b});
+    g_prof.push_back({name, launches, a, b});
 }
 
 }  // namespace iqw
@@ -44,7 +44,7 @@ void profile_push(const char* name, cudaEvent_t a, cudaEvent_t b) {
 extern "C" int iqw_abi_version(void) { return IQW_ABI_VERSION; }
 extern "C" const char* iqw_last_error(void) { return iqw::last_error_buffer(); }
 
-extern "C" int iqw_profile_enable(int on) { iqw::g_prof_on.store(on != 0); return IQW_OK; }
+extern "C" int iqw_profile_enable(int level) { iqw::g_prof_level.store(level < 0 ? 0 : level > 2 ? 2 : level); return IQW_OK; }
 
 extern "C" int iqw_profile_reset(void) {
     std::lock_guard<std::mutex> lock(iqw::g_prof_mutex);
@@ -62,7 +62,7 @@ extern "C" int iqw_profile_report(char* buf, size_t cap) {
         cudaError_t e = cudaEventElapsedTime(&ms, r.a, r.b);
         if (e != cudaSuccess) return iqw::fail(IQW_ERR_CUDA, "profile: %s", cudaGetErrorString(e));
         auto& x = agg[r.name];
-        x.first += 1;
+        x.first += r.launches;
         x.second += ms;
     }
     std::string out;

@@ -28,20 +28,29 @@ inline int fail(int code, const char* fmt, ...) {
 
 int device_sm_count(int* sms);
 
-// Optional per-kernel timing (off by default; bench.py turns it on): every launch site is wrapped
-// in a scope that records a CUDA event before and after the launch ON THE LAUNCHING STREAM.
-bool profile_enabled();
-void profile_push(const char* name, cudaEvent_t a, cudaEvent_t b);
+// Optional kernel timing (off by default): a launch site is wrapped in a scope that records a CUDA
+// event before and after it ON THE LAUNCHING STREAM.  Level 1 (what bench.py runs its timed region
+// under) times the heavy kernels one by one and the trains of small follow-up kernels as one scope
+// each -- ~12 events per persistence-spectrum step instead of ~46, which cost 2 % of the step;
+// level 2 times every launch (probes).  A scope carries the number of launches it covers.
+int profile_level();
+inline bool profile_enabled() { return profile_level() >= 1; }
+void profile_push(const char* name, int launches, cudaEvent_t a, cudaEvent_t b);
 struct ProfScope {
-    const char* name; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(const char* n, cudaStream_t st) : name(n), s(st) {
-        if (profile_enabled()) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    const char* name; cudaStream_t s; int n; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(const char* nm, cudaStream_t st, int launches, bool on) : name(nm), s(st), n(launches) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
     }
-    ~ProfScope() { if (a) { cudaEventRecord(b, s); profile_push(name, a, b); } }
+    ~ProfScope() { if (a) { cudaEventRecord(b, s); profile_push(name, n, a, b); } }
 };
 #define IQW_CAT2(a, b) a##b
 #define IQW_CAT(a, b) IQW_CAT2(a, b)
-#define IQW_PROFILE(name, stream) ::iqw::ProfScope IQW_CAT(_prof_, __LINE__)(name, stream)
+// one heavy launch: timed at every level
+#define IQW_PROFILE(name, stream) ::iqw::ProfScope IQW_CAT(_prof_, __LINE__)(name, stream, 1, ::iqw::profile_level() >= 1)
+// one small launch inside a train: timed at level 2 only
+#define IQW_PROFILE_FINE(name, stream) ::iqw::ProfScope IQW_CAT(_prof_, __LINE__)(name, stream, 1, ::iqw::profile_level() >= 2)
+// a train of n small launches as one scope: timed at level 1 only (level 2 times its members)
+#define IQW_PROFILE_TRAIN(name, stream, n) ::iqw::ProfScope IQW_CAT(_prof_, __LINE__)(name, stream, n, ::iqw::profile_level() == 1)
 
 // order-preserving map float32 -> uint32 (total order: -nan < -inf < ... < -0 < +0 < ... < +inf < nan)
 __host__ __device__ __forceinline__ uint32_t float_to_key(float f) {

@@ -1513,9 +1513,9 @@ static void launch_refine_levels(const Grid& g, cudaStream_t s, const float* p, 
     const size_t smem = sizeof(uint16_t) * M * kNSub * kBX;
     cudaFuncSetAttribute(refine_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int level = 0; level < kRefineLevels; ++level) {
-        { IQW_PROFILE(names[which][level], s);
+        { IQW_PROFILE_FINE(names[which][level], s);
           refine_kernel<M><<<g.grid, kBX, smem, s>>>(p, cols, rm, g.rows_per_split, w); }
-        { IQW_PROFILE(which ? "sample_scan" : "stats_scan", s);
+        { IQW_PROFILE_FINE(which ? "sample_scan" : "stats_scan", s);
           scan_refine_kernel<<<cblocks, cthreads, 0, s>>>(cols, rp, w); }
     }
 }
@@ -1523,7 +1523,7 @@ static void launch_refine_levels(const Grid& g, cudaStream_t s, const float* p, 
 template <int M>
 static void launch_collect(const Grid& g, cudaStream_t s, const float* p, long long cols, RowMap rm,
                            const Work& w, const char* name) {
-    IQW_PROFILE(name, s);
+    IQW_PROFILE_FINE(name, s);
     collect_kernel<M><<<g.grid, kBX, 0, s>>>(p, cols, rm, g.rows_per_split, w);
 }
 
@@ -1584,12 +1584,14 @@ static int run_exact(const float* p, long long cols, RowMap rm, const RankPlan& 
     long long rsplits = (rm.n + stride - 1) / stride / 64;
     if (rsplits < 1) rsplits = 1;
     if (rsplits > 64) rsplits = 64;
-    { IQW_PROFILE(sample ? "sample_range" : "stats_range", s);
+    // (range, l0, scan0, 7 x (refine, scan), collect, resolve)
+    IQW_PROFILE_TRAIN(sample ? "sample_exact" : "stats_exact", s, rp.n_ranks > 0 ? 3 + 2 * kRefineLevels + 2 : 2);
+    { IQW_PROFILE_FINE(sample ? "sample_range" : "stats_range", s);
       range_kernel<<<dim3((unsigned)col_tiles, (unsigned)rsplits), kBX, 0, s>>>(p, cols, rm, stride, w); }
 
     const size_t l0_smem = sizeof(uint16_t) * kNB0 * kBX;
     {
-        IQW_PROFILE(sample ? "sample_l0" : "stats_l0", s);
+        IQW_PROFILE_FINE(sample ? "sample_l0" : "stats_l0", s);
 #define IQW_L0(A, B, C)                                                                              \
     do {                                                                                             \
         cudaFuncSetAttribute(l0_kernel<A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l0_smem); \
@@ -1602,13 +1604,13 @@ static int run_exact(const float* p, long long cols, RowMap rm, const RankPlan& 
 #undef IQW_L0
     }
     if (rp.n_ranks > 0) {
-        { IQW_PROFILE(sample ? "sample_scan" : "stats_scan", s);
+        { IQW_PROFILE_FINE(sample ? "sample_scan" : "stats_scan", s);
           scan0_kernel<<<cblocks, cthreads, 0, s>>>(cols, rp, w); }
         IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, cols, rm, rp, w, cblocks, cthreads,
                                                            sample ? "sample" : "stats"));
         IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, cols, rm, w,
                                                      sample ? "sample_collect" : "stats_collect"));
-        { IQW_PROFILE(sample ? "sample_resolve" : "stats_resolve", s);
+        { IQW_PROFILE_FINE(sample ? "sample_resolve" : "stats_resolve", s);
           resolve_kernel<<<(unsigned)cols, kResolveThreads, 0, s>>>(cols, rp, w); }
     }
     IQW_CUDA_OK(cudaGetLastError());
@@ -1694,7 +1696,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
     for (int64_t c = 0; c < n_channels; ++c) {
         const float* p = d_p + c * p_channel_stride;
         float* out = d_out + c * (int64_t)n_stats * n_cols;
-        { IQW_PROFILE("stats_init", s); if (int rc = reset_work(w, s)) return rc; }
+        { IQW_PROFILE_FINE("stats_init", s); if (int rc = reset_work(w, s)) return rc; }
 
         if (!sampled) {
             if (int rc = run_exact(p, n_cols, full, rp, true, want_sum, to_dB != 0, eps, w, sms, s, false))
@@ -1704,7 +1706,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
               sample_brackets_kernel<<<(unsigned)((n_cols + kSampleCols - 1) / kSampleCols), kSampleThreads,
                                        kSampleSmem, s>>>(p, n_cols, lp.sample, lp.bp, w); }
             IQW_DISPATCH_G(lp.bp.n_groups, launch_bracket_pass<M>(s, p, n_cols, n_rows, lp, want_minmax, want_sum, to_dB != 0, eps, w));
-            { IQW_PROFILE("stats_scan", s);
+            { IQW_PROFILE_FINE("stats_scan", s);
               scan_brackets_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, n_rows, rp, lp.bp.n_groups, w); }
             IQW_DISPATCH_G(lp.bp.n_groups, if (int rc = launch_select<M>(s, n_cols, rp, lp, w)) return rc);
             // whatever select could not settle from the lists (missed brackets, overflowed lists,
@@ -1722,13 +1724,20 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
                 g.grid = dim3((unsigned)slots, (unsigned)splits);
                 g.rows_per_split = rps;
             }
+            // the train that settles what select left open (it exits at once when nothing is):
+            // scan_brackets (above) + 7 x (refine, scan) + collect + resolve, then finalize
+            IQW_PROFILE_TRAIN("stats_tail", s, 1 + 2 * kRefineLevels + 3);
             IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, n_cols, full, rp, w, cblocks, cthreads, "stats"));
             IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, n_cols, full, w, "stats_collect"));
-            { IQW_PROFILE("stats_resolve", s);
+            { IQW_PROFILE_FINE("stats_resolve", s);
               resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_cols, rp, w); }
+            { IQW_PROFILE_FINE("stats_finalize", s);
+              finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, w, out); }
         }
-        { IQW_PROFILE("stats_finalize", s);
-          finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, w, out); }
+        if (!sampled) {
+            IQW_PROFILE("stats_finalize", s);
+            finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, w, out);
+        }
         IQW_CUDA_OK(cudaGetLastError());
     }
     return IQW_OK;

@@ -12,7 +12,7 @@ n = 15_360_000
 x = bench.device_capture(torch, n, 1, torch.device('cuda', 0)).view(1, n)
 kw = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5, statistics=[0.5, 0.99], dB=True, axis=1)
 for it in range(3):
-    _lib.profile(it == 2)
+    _lib.profile(it == 2, fine=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); out = iqw.persistence_spectrum(x, **kw); e1.record(); torch.cuda.synchronize()
     print(f'call {it}: {e0.elapsed_time(e1):.3f} ms')

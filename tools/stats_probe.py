@@ -19,7 +19,7 @@ for stats in sel:
     cnt = []
     out = iqw.time_statistics(p, stats, dB=True, counters=cnt)
     torch.cuda.synchronize()
-    _lib.profile(True)
+    _lib.profile(True, fine=True)
     for _ in range(3):
         iqw.time_statistics(p, stats, dB=True)
     torch.cuda.synchronize()
