@@ -103,3 +103,32 @@ def test_no_cpu_fallback():
         pytest.skip('GPU present')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         iqw.spectrogram(np.zeros(1000, np.complex64), fs=1.0, window='hann', nperseg=64)
+
+
+def test_util_helpers_known_answers():
+    import torch
+    from iqwaveform_b200 import util as U
+    assert U.isroundmod(1e6, 1e3) and not U.isroundmod(1e6, 3e3) and U.isroundmod(0.3, 0.1)
+    assert list(U.isroundmod(np.array([1.0, 1.5]), 0.5)) == [True, True] and not U.isroundmod(np.array([1.1]), 0.5)[0]
+    assert U.find_float_inds(('0.5', 'mean', 0.1, '1e-3')) == [True, False, True, True]
+    for x, want in [(np.zeros(2, np.complex64), 'float32'), (np.zeros(2, np.complex128), 'float64'),
+                    (np.zeros(2, np.float16), 'float16'), (np.zeros(2, np.int32), 'float32'), (1.5, 'float64'),
+                    (torch.zeros(2, dtype=torch.complex64), 'float32'), (torch.zeros(2, dtype=torch.float64), 'float64')]:
+        assert U.float_dtype_like(x) == np.dtype(want)
+    assert U.float_dtype_like(np.zeros(2, np.float16), 'float32') == np.dtype('float32')
+    assert U.dtype_change_float(np.complex128, np.float32) is np.complex64
+    assert U.dtype_change_float('float64', 'complex64') is np.float32
+    with pytest.raises(ValueError):
+        U.dtype_change_float(np.int32, np.float32)
+    a = np.arange(24).reshape(2, 3, 4)
+    assert np.array_equal(U.axis_slice(a, 1, None, axis=1), a[:, 1:]) and np.array_equal(U.axis_slice(a, 0, 4, 2), a[..., 0:4:2])
+    assert np.array_equal(U.axis_index(a, np.array([True, False, True]), axis=1), a[:, [0, 2]])
+    assert U.to_blocks(a, 2, axis=2).shape == (2, 3, 2, 2) and U.to_blocks(a, 2, axis=-1).shape == (2, 3, 2, 2)
+    assert U.to_blocks(np.arange(10), 4, truncate=True).shape == (2, 4)
+    assert U.to_blocks(torch.arange(10), 5).shape == (2, 5)
+    with pytest.raises(ValueError):
+        U.to_blocks(np.arange(10), 4)
+    with pytest.raises(TypeError):
+        U.to_blocks(np.arange(10), 2.0)
+    with pytest.raises(IndexError):
+        U.to_blocks(np.zeros(0), 2)

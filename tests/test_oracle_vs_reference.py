@@ -217,3 +217,24 @@ def test_oaresample(shape, axis, kw):
     b = orc.oaresample(x.copy(), fs=1e6, axis=axis, window='hamming', **kw)
     assert a.shape == b.shape and a.dtype == b.dtype
     assert np.array_equal(a.view(np.float32), b.view(np.float32))
+
+
+def test_util_helpers_equal_the_reference():
+    """row U of SURVEY 8a: the product's host helpers against the reference's own (host logic only)"""
+    from iqwaveform_b200 import util as U
+    R = ref.util
+    for v, d in [(1e6, 1e3), (1e6, 3e3), (0.3, 0.1), (15.36e6, 15e3), (1.0, 0.3)]:
+        assert bool(U.isroundmod(v, d)) == bool(R.isroundmod(v, d))
+    seq = ('0.5', 'mean', 0.1, 'max', '1e-3')
+    assert U.find_float_inds(seq) == R.find_float_inds(seq)
+    for x in (np.zeros(2, np.complex64), np.zeros(2, np.complex128), np.zeros(2, np.float16), np.zeros(2, np.int32), 1.5):
+        for m in (None, 'float32', 'float64'):
+            assert U.float_dtype_like(x, m) == R.float_dtype_like(x, m)
+    for a, b in [(np.complex128, np.float32), (np.float64, np.float32), (np.complex64, np.float64), (np.float16, np.complex64)]:
+        assert U.dtype_change_float(a, b) == R.dtype_change_float(a, b)
+    a = np.arange(120).reshape(2, 3, 20)
+    for ax in (0, 1, 2, -1):
+        assert np.array_equal(U.axis_slice(a, 1, None, 2, axis=ax), R.axis_slice(a, 1, None, 2, axis=ax))
+    assert np.array_equal(U.axis_index(a, np.array([0, 2]), axis=1), R.axis_index(a, np.array([0, 2]), axis=1))
+    for size, ax, trunc in [(5, 2, False), (5, -1, False), (3, 2, True), (1, 0, False), (2, 0, False)]:
+        assert np.array_equal(U.to_blocks(a, size, truncate=trunc, axis=ax), R.to_blocks(a, size, truncate=trunc, axis=ax))
