@@ -16,10 +16,11 @@ from .fourier import (stft, istft, ola_filter, oaresample, iq_to_stft_spectrogra
                       get_window, equivalent_noise_bandwidth, time_statistics)
 from .power_analysis import (iq_to_bin_power, iq_to_cyclic_power, powtodB, dBtopow, envtopow, envtodB, dBlinmean, dBlinsum,
                              sample_ccdf)
-from .util import histogram_last_axis
+from .util import histogram_last_axis, isroundmod, to_blocks
+from ._plan import find_window_param_from_enbw
 
 __version__ = '0.1.0'
-__all__ = ['fourier', 'power_analysis', 'distributed', 'util', 'Domain', 'set_input_domain', 'get_input_domain', 'stft', 'istft', 'ola_filter', 'oaresample', 'iq_to_stft_spectrogram', 'channelize_power', 'sample_ccdf', 'histogram_last_axis', 'spectrogram', 'power_spectral_density',
+__all__ = ['fourier', 'power_analysis', 'distributed', 'util', 'Domain', 'set_input_domain', 'get_input_domain', 'stft', 'istft', 'ola_filter', 'oaresample', 'iq_to_stft_spectrogram', 'channelize_power', 'sample_ccdf', 'histogram_last_axis', 'isroundmod', 'to_blocks', 'find_window_param_from_enbw', 'spectrogram', 'power_spectral_density',
            'persistence_spectrum', 'fftfreq', 'get_window', 'equivalent_noise_bandwidth',
            'time_statistics', 'iq_to_bin_power', 'iq_to_cyclic_power', 'powtodB', 'dBtopow', 'envtopow', 'envtodB', 'dBlinmean',
            'dBlinsum']
