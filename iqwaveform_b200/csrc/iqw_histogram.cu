@@ -76,13 +76,20 @@ edge_count_kernel(const float* __restrict__ a, long long n_cols, const double* _
     const long long c0 = min(n_cols, per * blockIdx.y), c1 = min(n_cols, c0 + per);
     const bool vec = ((reinterpret_cast<uintptr_t>(src + c0) & 15) == 0);
     const long long nvec = vec ? (c1 - c0) >> 2 : 0;
-    for (long long i = threadIdx.x; i < nvec; i += kHiThreads) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + c0) + i);
+    const float4* src4 = reinterpret_cast<const float4*>(src + c0);
+    auto count4 = [&](const float4& v) {
         atomicAdd(&mine[classify<RIGHT>(e, n_edges, e0, inv, v.x)], 1u);
         atomicAdd(&mine[classify<RIGHT>(e, n_edges, e0, inv, v.y)], 1u);
         atomicAdd(&mine[classify<RIGHT>(e, n_edges, e0, inv, v.z)], 1u);
         atomicAdd(&mine[classify<RIGHT>(e, n_edges, e0, inv, v.w)], 1u);
+    };
+    long long i = threadIdx.x;
+    for (; i + 3 * kHiThreads < nvec; i += 4 * kHiThreads) {      // four 16-byte loads in flight per thread
+        const float4 v0 = __ldcs(src4 + i), v1 = __ldcs(src4 + i + kHiThreads);
+        const float4 v2 = __ldcs(src4 + i + 2 * kHiThreads), v3 = __ldcs(src4 + i + 3 * kHiThreads);
+        count4(v0); count4(v1); count4(v2); count4(v3);
     }
+    for (; i < nvec; i += kHiThreads) count4(__ldcs(src4 + i));
     for (long long k = c0 + nvec * 4 + threadIdx.x; k < c1; k += kHiThreads)
         atomicAdd(&mine[classify<RIGHT>(e, n_edges, e0, inv, src[k])], 1u);
     __syncthreads();
