@@ -120,3 +120,18 @@ def test_frame_permutation_invariance(cuda_device):
     a = iqw.persistence_spectrum(x.view(1, -1), **kw)
     b = iqw.persistence_spectrum(xp.view(1, -1), **kw)
     assert torch.equal(a, b)
+
+
+def test_channels_pipelined_on_two_streams_equal_one_by_one():
+    """(C, N) input large enough for the two-stream pipeline over channels: same bits as channel by channel"""
+    import iqwaveform_b200.fourier as F
+    g = torch.Generator('cuda').manual_seed(77)
+    x = torch.randn((3, 1 << 25), dtype=torch.complex64, device='cuda', generator=g)
+    kw = dict(fs=1e8, window='hann', resolution=1e8 / 2048, fractional_overlap=0.5,
+              statistics=[0.1, 0.5, 'mean', 0.999, 'max'], dB=True, axis=1)
+    assert (x.shape[1] // 1024) * 2048 * 4 >= F.PIPELINE_MIN_BYTES
+    together = iqw.persistence_spectrum(x, **kw)
+    single = torch.stack([iqw.persistence_spectrum(x[c], **dict(kw, axis=0)) for c in range(3)])
+    assert torch.equal(together, single)
+    # the caller's stream sees finished results: an immediate consumer on it is correct
+    assert torch.equal(iqw.persistence_spectrum(x, **kw) + 0, single)

@@ -60,6 +60,17 @@ def main():
     rows.append(row('configs[0] persistence_spectrum 15.36 MS/s x 1 s nfft 1024 hann 50% q=[0.5,0.99]', n, ms, 24))
     del x
 
+    # configs[2] with several channels on ONE GPU (the bench line is one channel per GPU): the chains of
+    # consecutive channels run on two alternating streams
+    if not a.quick:
+        n = 1_000_000_000
+        xs = torch.stack([bench.device_capture(torch, n, 10 + c, dev) for c in range(4)])
+        ms = timed(lambda: iqw.persistence_spectrum(xs, fs=100e6, window='hann', resolution=100e6 / 4096,
+                                                    fractional_overlap=0.5, statistics=[0.1, 0.5, 0.9, 0.999], dB=True, axis=1))
+        rows.append(row('configs[2] persistence_spectrum, 4 channels x 1e9 samples on one GPU (two-stream channel pipeline)',
+                        4 * n, ms, 24))
+        del xs
+
     # configs[1]
     n = 100_000_000 if a.quick else 1_000_000_000
     x = bench.device_capture(torch, n, 2, dev)
