@@ -538,7 +538,7 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
     # Several channels: the STFT -> statistics chains of consecutive channels run on two alternating
     # streams with a spectrogram buffer each, so that the tail of one channel's statistics (ALU /
     # issue bound, partly idle SMs) overlaps the next channel's STFT (FMA / shared-memory bound):
-    # 4-5 % more throughput at config-3 size, bit-identical results.  Needs room for two spectrograms.
+    # 3-4 % more throughput at config-3 size, bit-identical results.  Needs room for two spectrograms.
     if C >= 2 and spg_bytes >= PIPELINE_MIN_BYTES and torch.cuda.mem_get_info(dev)[0] > 2.5 * spg_bytes:
         main = torch.cuda.current_stream(dev)
         pair = _channel_streams.get(dev.index)
