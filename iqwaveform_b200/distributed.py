@@ -132,7 +132,7 @@ def bind_to_gpu_numa_node(device_index: int) -> str | None:
             return None
         os.sched_setaffinity(0, cpus)
         return cpulist
-    except (OSError, ValueError, AttributeError, RuntimeError):
+    except Exception:       # no GPU, no sysfs, restricted cpuset ...: binding is an optimisation only
         return None
 
 

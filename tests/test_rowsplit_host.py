@@ -63,3 +63,13 @@ def test_requires_total_rows_when_sharded():
     tg = D.ThreadGroup(2)
     with pytest.raises(ValueError):
         D.select_order_statistics(torch.zeros(4, 2), [1], group=tg.member(0), ops=NumpyShardOps())
+
+
+def test_numa_binding_is_best_effort():
+    import os
+    before = os.sched_getaffinity(0)
+    got = D.bind_to_gpu_numa_node(0)          # no GPU here: must not raise and must not change anything
+    assert got is None or isinstance(got, str)
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
