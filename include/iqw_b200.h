@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IQW_ABI_VERSION 6
+#define IQW_ABI_VERSION 7
 
 typedef enum iqw_status {
     IQW_OK = 0,
@@ -176,6 +176,15 @@ int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t
                   int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
                   const void* d_bin_gain, float scale, void* d_out, int64_t out_channel_stride,
                   void* stream);
+
+/* Plain batched inverse DFT of row A4's public pair fft / ifft (fourier.py:221-246, the scipy.fft.ifft
+ * / cuFFT-inverse call): out[r][n] = 1/nfft * sum_k y[r][k] * exp(+2*pi*i*k*n/nfft), bins and samples
+ * in NATURAL order.  Kernel 4 with hop = nfft and without the (-1)^n of the baked-in shift.  d_y and
+ * d_out are (n_rows, nfft) complex64, C-contiguous; nfft a power of two, 16..8192.  (The forward
+ * transform of fourier.py:200-218 needs no entry of its own: iqw_stft_c64 with an all-ones window,
+ * hop = nfft, n_frames = n_rows and mode COMPLEX is the unnormalised natural-order DFT of every row,
+ * for nfft up to 65536.) */
+int iqw_ifft_c64(const void* d_y, int64_t n_rows, int32_t nfft, void* d_out, void* stream);
 
 /* The whole of ola_filter (fourier.py:1108-1181 with nfft_out == nfft) in ONE kernel: overlapped
  * frame gather * window -> FFT -> zero the bins outside [bin_lo, bin_hi) -> inverse FFT -> (-1)^n ->

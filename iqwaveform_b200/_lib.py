@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libiqw_b200.so')
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # statuses / enums mirrored from include/iqw_b200.h
 IQW_OK = 0
@@ -57,6 +57,7 @@ SIGNATURES = {
     'iqw_elementwise_f32': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i32, _f32, _vp]),
     'iqw_elementwise_c64': (ctypes.c_int, [_i32, _vp, _vp, _i64, _f32, _vp]),
     'iqw_istft_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _i64, _vp]),
+    'iqw_ifft_c64': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     'iqw_ola_filter_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     'iqw_edge_counts_f32': (ctypes.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp]),
     'iqw_bracket_collect_workspace_bytes': (_sz, [_i64, _i64]),

@@ -33,6 +33,7 @@ struct IstftArgs {
     int y_off;                // bin index of the first stored bin (0, or bin_lo)
     const float2* gain;       // optional per-bin complex gain (frequency-domain FIR), or null
     float scale;              // factor applied to every output sample after the overlap-add
+    int natural;              // != 0: bins in natural (unshifted) order, no (-1)^n on the samples (plain ifft)
     float2* out;
     long long out_ch_stride;
     const float2* twiddle;
@@ -72,8 +73,8 @@ istft_kernel(const IstftArgs a) {
     const float2* src = a.y + c * a.y_ch_stride + ltid;
     float2* dst = a.out + c * a.out_ch_stride + ltid;
     // conj(FFT(conj(Y))) / N, and the (-1)^n of sample n = ltid + j*TPF
-    const float s_even = 1.0f / (float)N, s_odd = (TPF & 1) ? -s_even : s_even;
-    const float sg = (ltid & 1) ? -1.0f : 1.0f;
+    const float s_even = 1.0f / (float)N, s_odd = ((TPF & 1) && !a.natural) ? -s_even : s_even;
+    const float sg = ((ltid & 1) && !a.natural) ? -1.0f : 1.0f;
 
     float2 acc[A > 0 ? A : 1];
 #pragma unroll
@@ -363,10 +364,10 @@ static int launch_istft(const IstftArgs& a, int log2r, cudaStream_t s) {
 
 using namespace iqw;
 
-extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t y_channel_stride,
-                             int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
-                             const void* d_bin_gain, float scale, void* d_out, int64_t out_channel_stride,
-                             void* stream) {
+static int istft_entry(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t y_channel_stride,
+                       int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
+                       const void* d_bin_gain, float scale, int natural, void* d_out,
+                       int64_t out_channel_stride, void* stream) {
     if (!d_y || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (nfft < 2 || (nfft & (nfft - 1)))
         return fail(IQW_ERR_UNSUPPORTED, "nfft=%d: only powers of two are built", nfft);
@@ -390,7 +391,7 @@ extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_fram
     a.y = (const float2*)d_y; a.y_ch_stride = y_channel_stride; a.n_channels = (int)n_channels;
     a.n_frames = n_frames; a.bin_lo = bin_lo; a.bin_hi = bin_hi;
     a.y_row = y_bins; a.y_off = y_bins == nfft ? 0 : bin_lo;
-    a.gain = (const float2*)d_bin_gain; a.scale = scale;
+    a.gain = (const float2*)d_bin_gain; a.scale = scale; a.natural = natural;
     a.out = (float2*)d_out; a.out_ch_stride = out_channel_stride;
     a.streams_per_ch = a.frames_per_stream = 0;
     if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;
@@ -407,6 +408,22 @@ extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_fram
         case 13: return launch_istft<13>(a, log2r, s);
     }
     return fail(IQW_ERR_UNSUPPORTED, "istft: nfft=%d", nfft);
+}
+
+extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_frames, int64_t y_channel_stride,
+                             int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
+                             const void* d_bin_gain, float scale, void* d_out, int64_t out_channel_stride,
+                             void* stream) {
+    return istft_entry(d_y, n_channels, n_frames, y_channel_stride, nfft, hop, bin_lo, bin_hi, y_bins,
+                       d_bin_gain, scale, 0, d_out, out_channel_stride, stream);
+}
+
+// plain batched inverse DFT (1/nfft normalised, natural bin order in, natural sample order out):
+// kernel 4 with hop = nfft (nothing to overlap-add) and without the (-1)^n of the baked-in shift
+extern "C" int iqw_ifft_c64(const void* d_y, int64_t n_rows, int32_t nfft, void* d_out, void* stream) {
+    if (n_rows < 1) return fail(IQW_ERR_INVALID, "ifft: need at least one row");
+    return istft_entry(d_y, 1, n_rows, n_rows * (int64_t)nfft, nfft, nfft, 0, nfft, nfft, nullptr, 1.0f, 1,
+                       d_out, n_rows * (int64_t)nfft, stream);
 }
 
 extern "C" int iqw_ola_filter_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,

@@ -26,7 +26,7 @@ from . import _arrays, _lib, _plan
 from .util import Domain, get_input_domain
 from ._plan import INF
 
-__all__ = ['stft', 'istft', 'ola_filter', 'oaresample', 'iq_to_stft_spectrogram', 'channelize_power', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
+__all__ = ['fft', 'ifft', 'zero_stft_by_freq', 'stft', 'istft', 'ola_filter', 'oaresample', 'iq_to_stft_spectrogram', 'channelize_power', 'spectrogram', 'power_spectral_density', 'persistence_spectrum',
            'fftfreq', 'get_window', 'equivalent_noise_bandwidth']
 
 fftfreq = _plan.fftfreq
@@ -205,6 +205,105 @@ def _istft_device(y3: torch.Tensor, nfft: int, noverlap: int, bin_lo: int = 0, b
         ctypes.c_void_p(gain.data_ptr()) if gain is not None else None, float(scale),
         ctypes.c_void_p(out.data_ptr()), n_out, _stream_ptr(y3.device)))
     return out
+
+
+_ones_cache: dict = {}
+
+
+def _check_fft_size(n: int, largest: int, what: str) -> None:
+    if n < 16 or n > largest or n & (n - 1):
+        raise NotImplementedError(f'{what}: transform size {n}: powers of two from 16 to {largest} are built')
+
+
+def fft(x, axis=-1, out=None, overwrite_x=False, plan=None, workers=None):
+    """forward complex DFT along `axis`, unnormalised, natural bin order; same arguments as the
+    reference (fourier.py:200-218, where it is scipy.fft.fft or cuFFT).  Runs kernel 1 with an
+    all-ones window and hop = nfft, so every row of the batch is one "frame".  `plan` and `workers`
+    are accepted and ignored (no FFT library is involved); `overwrite_x` is ignored (the kernel needs
+    no scratch).  complex64, power-of-two sizes 16..65536."""
+    xd, res = _arrays.to_device(x)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+    if x2.dtype != torch.complex64:
+        raise NotImplementedError(f'only complex64 input is built (got {x2.dtype})')
+    R, n = x2.shape
+    _check_fft_size(n, 65536, 'fft')
+    if x2.numel() == 0:
+        raise IndexError('cannot transform arrays of size 0')
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    key = (n, x2.device.index)
+    with _window_lock:
+        w = _ones_cache.get(key)
+        if w is None:
+            w = _ones_cache[key] = torch.ones(n, dtype=torch.float32, device=x2.device)
+    direct = out is not None and not trail and isinstance(out, torch.Tensor) and out.is_cuda \
+        and out.dtype == torch.complex64 and out.is_contiguous() and out.numel() == x2.numel()
+    y = out.view(R, n) if direct else torch.empty((R, n), dtype=torch.complex64, device=x2.device)
+    ws_bytes = _lib.lib.iqw_stft_workspace_bytes(n, 1, R)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device) if ws_bytes else None
+    _lib.check(_lib.lib.iqw_stft_c64(
+        ctypes.c_void_p(x2.data_ptr()), 1, R * n, R * n, ctypes.c_void_p(w.data_ptr()), n, n, R,
+        _lib.STFT_COMPLEX, 0.0, 0, n, ctypes.c_void_p(y.data_ptr()), R * n,
+        ctypes.c_void_p(ws.data_ptr()) if ws_bytes else None, ws_bytes, _stream_ptr(x2.device)))
+    if direct:
+        return out
+    y = res.give_back(_arrays.restore_layout(y, lead, trail, 1))
+    if out is not None:         # any other `out` the reference would accept: filled by a copy
+        out[...] = y if isinstance(out, torch.Tensor) else np.asarray(y)
+        return out
+    return y
+
+
+def ifft(x, axis=-1, out=None, overwrite_x=False, plan=None, workers=None):
+    """inverse complex DFT along `axis`, scaled by 1/n, natural order; same arguments as the reference
+    (fourier.py:221-246).  Runs kernel 4 with hop = nfft and without the fft-shift sign
+    (``iqw_ifft_c64``).  complex64, power-of-two sizes 16..8192."""
+    xd, res = _arrays.to_device(x)
+    x2, lead, trail = _arrays.as_channels(xd, axis)
+    if x2.dtype != torch.complex64:
+        raise NotImplementedError(f'only complex64 input is built (got {x2.dtype})')
+    R, n = x2.shape
+    _check_fft_size(n, 8192, 'ifft')
+    if x2.numel() == 0:
+        raise IndexError('cannot transform arrays of size 0')
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    direct = out is not None and not trail and isinstance(out, torch.Tensor) and out.is_cuda \
+        and out.dtype == torch.complex64 and out.is_contiguous() and out.numel() == x2.numel()
+    y = out.view(R, n) if direct else torch.empty((R, n), dtype=torch.complex64, device=x2.device)
+    _lib.check(_lib.lib.iqw_ifft_c64(ctypes.c_void_p(x2.data_ptr()), R, n, ctypes.c_void_p(y.data_ptr()),
+                                     _stream_ptr(x2.device)))
+    if direct:
+        return out
+    y = res.give_back(_arrays.restore_layout(y, lead, trail, 1))
+    if out is not None:
+        out[...] = y if isinstance(out, torch.Tensor) else np.asarray(y)
+        return out
+    return y
+
+
+def zero_stft_by_freq(freqs, xstft, *, passband, axis=0):
+    """band-pass in the STFT domain by zeroing bins IN PLACE; same arguments as the reference
+    (fourier.py:707-720).  Device STFTs only (it is a memset of two bin ranges; inside `ola_filter`
+    the same mask is a read predicate of kernel 4 and costs nothing).  `axis` is the frame axis, the
+    bin axis follows it; like the reference, the bin spacing comes from `freqs` and the sample rate
+    is taken as ``xstft.shape[axis] * freq_step``."""
+    if not (isinstance(xstft, torch.Tensor) and xstft.is_cuda):
+        raise TypeError('zero_stft_by_freq works in place on a device STFT (torch CUDA tensor)')
+    freqs = np.asarray(freqs)
+    freq_step = float(freqs[1] - freqs[0])
+    fs = xstft.shape[axis] * freq_step
+    if passband[0] is None or passband[1] is None:
+        # the reference turns a None edge into slice(0, None) / slice(None, None) and clears the whole
+        # STFT (fourier.py:717-718); reproduced, not repaired (ola_filter never gets here: its
+        # passband arithmetic raises TypeError on None first)
+        return xstft.zero_()
+    ilo, ihi = _plan.freq_band_edges(freqs.size, fs, *passband)
+    nb = xstft.shape[axis + 1]
+    ilo, ihi = min(ilo, nb), min(ihi, nb)
+    xstft.narrow(axis + 1, 0, ilo).zero_()
+    xstft.narrow(axis + 1, ihi, nb - ihi).zero_()
+    return xstft
 
 
 def _trim_center(x: torch.Tensor, size, axis: int) -> torch.Tensor:

@@ -238,3 +238,21 @@ def test_util_helpers_equal_the_reference():
     assert np.array_equal(U.axis_index(a, np.array([0, 2]), axis=1), R.axis_index(a, np.array([0, 2]), axis=1))
     for size, ax, trunc in [(5, 2, False), (5, -1, False), (3, 2, True), (1, 0, False), (2, 0, False)]:
         assert np.array_equal(U.to_blocks(a, size, truncate=trunc, axis=ax), R.to_blocks(a, size, truncate=trunc, axis=ax))
+
+
+@pytest.mark.parametrize('n', [16, 100, 1024, 8192])
+def test_fft_ifft(n):
+    """row A4's public pair (fourier.py:200-246)"""
+    x = synth(n, (3, n))
+    assert np.array_equal(ref.fourier.fft(x.copy(), axis=1).view(np.float32), orc.fft(x, axis=1).view(np.float32))
+    assert np.array_equal(ref.fourier.ifft(x.copy(), axis=1).view(np.float32), orc.ifft(x, axis=1).view(np.float32))
+    assert np.array_equal(ref.fourier.fft(x.T.copy(), axis=0), orc.fft(x.T.copy(), axis=0))
+
+
+@pytest.mark.parametrize('passband', [(-0.2e6, 0.1e6), (-3.0, 2.0), (-1e9, 1e9), (None, 2.0), (-3.0, None)])
+def test_zero_stft_by_freq(passband):
+    x = synth(5, (2, 9000))
+    f, _, y = ref.fourier.stft(x, fs=1e6, window='hamming', nperseg=256, noverlap=128, axis=1)
+    a = ref.fourier.zero_stft_by_freq(f, y.copy(), passband=passband, axis=1)
+    b = orc.zero_stft_by_freq(f, y.copy(), passband=passband, axis=1)
+    assert np.array_equal(a.view(np.float32), b.view(np.float32))
