@@ -114,6 +114,14 @@ def main():
         rows.append(row(f'(f3) ola_filter nfft {nfft} hamming, one kernel', n, ms, 16))
         ms = timed(lambda: iqw.ola_filter(x, fs=1e8, nfft=nfft, window='hamming', passband=(-2e7, 2e7), fused=False))
         rows.append(row(f'(f3) ola_filter nfft {nfft} hamming, stft + istft kernels', n, ms, 48))
+    # row A4's public pair: batched fft / ifft of (rows, n) complex64, 8 B read + 8 B written per sample
+    for nfft in (256, 1024, 4096, 65536):
+        xr = x.view(-1, nfft)
+        ms = timed(lambda: iqw.fft(xr, axis=1))
+        rows.append(row(f'(A4) fft rows of {nfft}', n, ms, 16))
+        if nfft <= 8192:
+            ms = timed(lambda: iqw.ifft(xr, axis=1))
+            rows.append(row(f'(A4) ifft rows of {nfft}', n, ms, 16))
     if a.out:
         json.dump({'hbm_peak_GBps': PEAK, 'rows': rows}, open(a.out, 'w'), indent=1)
 
