@@ -97,3 +97,18 @@ def test_zero_stft_by_freq_bit_exact(passband):
     assert np.array_equal(got.cpu().numpy().view(np.float32), want.view(np.float32))
     with pytest.raises(TypeError):
         iqw.zero_stft_by_freq(f, y, passband=passband, axis=1)
+
+
+@pytest.mark.parametrize('n,rows', [(16, 1), (64, 7), (1024, 3), (4096, 5), (8192, 2)])
+def test_no_write_outside_the_output(n, rows):
+    """compute-sanitizer is not available on the GPU pool: the outputs sit between guard bands"""
+    x = torch.from_numpy(synth(n + rows, (rows, n))).cuda()
+    guard = 4096
+    for fn in (iqw.fft, iqw.ifft):
+        buf = torch.full((rows * n + 2 * guard,), complex(123.0, -321.0), dtype=torch.complex64, device='cuda')
+        out = buf[guard:guard + rows * n].view(rows, n)
+        assert out.is_contiguous()
+        fn(x, axis=1, out=out)
+        torch.cuda.synchronize()
+        assert torch.all(buf[:guard] == complex(123.0, -321.0)) and torch.all(buf[-guard:] == complex(123.0, -321.0))
+        assert torch.equal(out, fn(x, axis=1))
