@@ -877,7 +877,8 @@ resolve_kernel(long long cols, RankPlan rp, Work w) {
 constexpr int kSampleThreads = 512;
 constexpr int kSR = 2 * kMaxGroups;   // sample ranks per column
 constexpr size_t kSampleSmem =
-    sizeof(uint32_t) * ((size_t)kSampleCols * kSampleRows + (size_t)kSampleCols * kSR * kSubBins);
+    sizeof(uint32_t) * ((size_t)kSampleCols * kSampleRows + (size_t)kSampleCols * kSR * kSubBins) +
+    (size_t)kSampleCols * kSelBins;            // + one byte per level-1 bin: which level-2 histogram it feeds
 static_assert(kSampleCols * kSR * kSubBins >= kSampleCols * kSelBins, "level-1 bins reuse the level-2 area");
 
 __device__ __forceinline__ uint32_t sel_shift(uint32_t span, uint32_t bins) {
@@ -892,6 +893,7 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
     uint32_t* keys = smem_u32;                                   // [kSampleCols][kSampleRows]
     uint32_t* hist = keys + kSampleCols * kSampleRows;           // level 1: [kSampleCols][kSelBins]
                                                                  // level 2: [kSampleCols][kSR][kSubBins]
+    unsigned char* slot_of_bin = reinterpret_cast<unsigned char*>(hist + kSampleCols * kSR * kSubBins);
     __shared__ uint32_t s_min[kSampleCols], s_max[kSampleCols];
     __shared__ uint32_t s_bin[kSampleCols][kSR], s_below[kSampleCols][kSR], s_slot[kSampleCols][kSR];
     __shared__ uint32_t s_elo[kSampleCols][kSR], s_ehi[kSampleCols][kSR];
@@ -988,6 +990,15 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
             s_slot[t][j] = (j > 0 && s_bin[t][j] == s_bin[t][j - 1]) ? s_slot[t][j - 1] : (uint32_t)j;
     }
     for (int i = t; i < kSampleCols * kSR * kSubBins; i += kSampleThreads) hist[i] = 0;
+    for (int i = t; i < kSampleCols * kSelBins / 4; i += kSampleThreads)
+        reinterpret_cast<uint32_t*>(slot_of_bin)[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    // level-1 bin -> the level-2 histogram it feeds (0xFF: none), so that the level-2 sweep is one
+    // byte lookup per key instead of a walk over the sample ranks
+    if (t < kSampleCols && c0 + t < cols) {
+        for (int j = nsr - 1; j >= 0; --j)              // descending: the first rank of a bin wins
+            if (s_bin[t][j] < (uint32_t)kSelBins) slot_of_bin[t * kSelBins + s_bin[t][j]] = (unsigned char)s_slot[t][j];
+    }
     __syncthreads();
 
     // ---- level 2: kSubBins sub-bins inside each wanted bin ----
@@ -998,12 +1009,8 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
             const uint32_t d = keys[c * kSampleRows + i] - kmin[c];
             const uint32_t b = d >> sh1[c];
             const uint32_t sh2 = sh1[c] > 8 ? sh1[c] - 8 : 0;
-            for (int j = 0; j < nsr; ++j) {
-                if (s_bin[c][j] == b && s_slot[c][j] == (uint32_t)j) {
-                    atomicAdd(&hist[(c * kSR + j) * kSubBins + ((d - (b << sh1[c])) >> sh2)], 1u);
-                    break;
-                }
-            }
+            const uint32_t j = slot_of_bin[c * kSelBins + b];
+            if (j != 0xFFu) atomicAdd(&hist[(c * kSR + j) * kSubBins + ((d - (b << sh1[c])) >> sh2)], 1u);
         }
     }
     __syncthreads();
