@@ -24,8 +24,14 @@ if os.path.exists(launches):
     per = collections.OrderedDict()
     ours = [r for r in rows if r.get('Metric Name') == 'gpu__time_duration.sum']
     # keep the last complete step: from the last stft_kernel launch on
-    last = max((i for i, r in enumerate(ours) if 'stft_kernel' in r['Kernel Name']), default=0)
-    ours = ours[last:]
+    # (the whole-capture launches, not the short per-chunk ones of the host-input (e2e) path that follow)
+    def _us(r):
+        return float(r['Metric Value'].replace(',', '')) * {'ns': 1e-3, 'us': 1, 'ms': 1e3, 'usecond': 1, 'nsecond': 1e-3, 'msecond': 1e3}.get(r['Metric Unit'], 1)
+    stft = [i for i, r in enumerate(ours) if 'stft_kernel' in r['Kernel Name']]
+    longest = max((_us(ours[i]) for i in stft), default=0.0)
+    last = max((i for i in stft if _us(ours[i]) >= 0.5 * longest), default=0)
+    nxt = min((i for i in stft if i > last), default=len(ours))
+    ours = ours[last:nxt]
     with open(os.path.join(out, f'launches_{tag}.csv'), 'w') as f:
         f.write('id,kernel,grid,block,duration_us\n')
         for r in ours:
