@@ -1145,20 +1145,29 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
         for (int i = t; i < M * kSelBins; i += kSelThreads) hist[i] = 0;
         __syncthreads();
         {   // bracket parameters in registers for the sweep (a bracket not in SEL_HIST gets an empty range)
-            uint32_t ra[M], rw[M], rsh[M];
+            // The brackets are disjoint, so a key feeds at most one histogram: the bin index is
+            // selected with predicated minima and ONE shared atomic follows (a branch and an atomic
+            // per bracket cost 57 instructions per key, this costs about half).  A bracket that is
+            // not being histogrammed gets the one-key range [0xFFFFFFFF, 0xFFFFFFFF] and an offset
+            // beyond the histograms, so that even that key cannot hide the match of a live bracket.
+            uint32_t ra[M], rw[M], rsh[M], goff[M];
 #pragma unroll
             for (int g = 0; g < M; ++g) {
                 const bool on = s_mode[g] == SEL_HIST;
                 ra[g] = on ? s_a[g] : 0xFFFFFFFFu;
                 rw[g] = on ? s_b[g] - s_a[g] : 0u;          // k in [a, b]  <=>  k - a <= b - a (unsigned)
-                rsh[g] = s_sh[g];
+                rsh[g] = on ? s_sh[g] : 0u;
+                goff[g] = on ? (uint32_t)(g * kSelBins) : 0x80000000u;
             }
             sweep([&](uint32_t k) {
+                uint32_t idx = 0xFFFFFFFFu;
 #pragma unroll
                 for (int g = 0; g < M; ++g) {
                     const uint32_t d = k - ra[g];
-                    if (d <= rw[g] && ra[g] != 0xFFFFFFFFu) atomicAdd(&hist[g * kSelBins + (d >> rsh[g])], 1u);
+                    const uint32_t v = goff[g] + (d >> rsh[g]);
+                    if (d <= rw[g]) idx = min(idx, v);
                 }
+                if (idx < (uint32_t)(M * kSelBins)) atomicAdd(&hist[idx], 1u);
             });
         }
         __syncthreads();
@@ -1262,7 +1271,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
 
     // ---- second sweep: the keys of the target bins ----
     {   // key range of the target bins of every collecting bracket, in registers
-        uint32_t ra[M], rw[M];
+        uint32_t ra[M], rw[M], tag[M];
 #pragma unroll
         for (int g = 0; g < M; ++g) {
             const bool on = s_mode[g] == SEL_COLLECT;
@@ -1272,14 +1281,16 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
             if (hi > (unsigned long long)s_b[g]) hi = s_b[g];
             ra[g] = on ? lo : 0xFFFFFFFFu;
             rw[g] = on ? (uint32_t)hi - lo : 0u;
+            tag[g] = on ? (uint32_t)g : 0x80000000u;       // same scheme as the histogram sweep
         }
         sweep([&](uint32_t k) {
+            uint32_t gm = 0xFFFFFFFFu;
 #pragma unroll
-            for (int g = 0; g < M; ++g) {
-                if (k - ra[g] <= rw[g] && ra[g] != 0xFFFFFFFFu) {
-                    const uint32_t pos = atomicAdd(&s_n[g], 1u);
-                    if (pos < (uint32_t)kSelBuf) buf[g * kSelBuf + pos] = k;
-                }
+            for (int g = 0; g < M; ++g)
+                if (k - ra[g] <= rw[g]) gm = min(gm, tag[g]);
+            if (gm < (uint32_t)M) {
+                const uint32_t pos = atomicAdd(&s_n[gm], 1u);
+                if (pos < (uint32_t)kSelBuf) buf[gm * kSelBuf + pos] = k;
             }
         });
     }
