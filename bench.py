@@ -16,9 +16,13 @@ A step = one full pass of the hot path over one channel per GPU:
            device->host read of the result inside the timed region).
 `roofline`: dominant kernel's algorithmic bytes / its measured duration (library profile events
            recorded inside the timed region) against MEASURED_PEAKS.json.
-`cpu_baseline`: the numpy/scipy oracle port of the reference (same library calls as the
-           reference: scipy.fft with cpu_count//2 workers, np.quantile) on a bounded sample.
---impl reference times that CPU port alone (rank 0), as the reference arm.
+`cpu_baseline`: the reference's own power_spectral_density (unmodified package installed to
+           baseline/_ref by __graft_entry__.build(), imported through oracle/ref_shim.py;
+           kind "reference") on a bounded sample of the workload; the numpy/scipy oracle port
+           (kind "port") only when baseline/_ref is absent.
+--impl reference times that CPU arm alone (rank 0), as the reference arm.
+`extra.configs`: one-shot timings (best of 3) of BASELINE configs[1], configs[3] (30 s half-capture)
+           and the configs[4] sweep, N = 1 only.
 """
 from __future__ import annotations
 
@@ -46,12 +50,18 @@ UNIT = 'GS/s'
 
 
 def workload_config(n_gpus, samples):
+    """the workload both arms name (identical in the GPU and the reference line).  The GPU arm processes
+    it in full every step; the CPU arms process the bounded sample stated under `cpu_arms_step`."""
     return {
         'workload': 'BASELINE configs[2] persistence_spectrum, sharded by channel: 1 channel per GPU',
         'channels': n_gpus, 'channels_per_gpu': 1, 'samples_per_channel': samples,
         'sample_rate_hz': FS, 'nfft': NFFT, 'window': WINDOW, 'overlap': OVERLAP,
         'statistics': STATS, 'dB': True,
         'frames_per_channel': (samples - NFFT) // (NFFT // 2) + 1,
+        'cpu_arms_step': {'what': 'cpu_baseline and --impl reference: ONE CPU process (rank 0 at every N) on a '
+                                  'bounded sample of one channel per step, same nfft/window/overlap/statistics',
+                          'channels': 1, 'samples_per_channel': CPU_SAMPLE,
+                          'frames_per_channel': (CPU_SAMPLE - NFFT) // (NFFT // 2) + 1},
         'l2': 'no flush: per-step input (8 B/sample) and spectrogram (8 B/sample) exceed the 126 MB L2',
         'collective': 'nccl all_gather of the (4, 4096) fp32 result per channel' if n_gpus > 1 else 'none',
     }
@@ -76,40 +86,64 @@ def cpu_capture(n, seed=1234):
     return x
 
 
-def cpu_step(x):
+def reference_api():
+    """-> (persistence-spectrum callable, kind).  kind "reference": the UNMODIFIED reference package
+    (fourier.py:1236-1327, stock code path) from /root/reference or its installed copy baseline/_ref;
+    kind "port": the numpy/scipy oracle restatement, only when neither is present"""
+    from oracle import ref_shim
+
+    ref = ref_shim.load()
+    if ref is not None:
+        return ref.fourier.power_spectral_density, 'reference'
     from oracle import iqw_oracle as orc
 
-    return orc.persistence_spectrum(x[None, :], fs=FS, window=WINDOW, resolution=FS / NFFT,
-                                    fractional_overlap=OVERLAP, statistics=STATS, dB=True, axis=1)
+    return orc.persistence_spectrum, 'port'
+
+
+def cpu_step(x, fn=None):
+    fn = fn or reference_api()[0]
+    return fn(x[None, :], fs=FS, window=WINDOW, resolution=FS / NFFT, fractional_overlap=OVERLAP,
+              statistics=STATS, dB=True, axis=1)
 
 
 def cpu_cores():
     return max((os.cpu_count() or 1) // 2, 1)
 
 
+def cpu_sample_note(kind):
+    what = ('the reference\'s own iqwaveform.fourier.power_spectral_density, unmodified (baseline/_ref)'
+            if kind == 'reference' else 'numpy/scipy oracle port of the reference (baseline/_ref absent)')
+    return (f'1 channel x {CPU_SAMPLE} samples per step ({CPU_SAMPLE / FS:.3f} s of the 10 s capture), same '
+            f'nfft/overlap/statistics; {what}; scipy.fft workers = cpu_count//2 = {cpu_cores()} of '
+            f'{os.cpu_count()} cores (the reference policy, fourier.py:214), numpy stages single-threaded '
+            f'as in the reference')
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
+    fn, kind = reference_api()
     x = cpu_capture(CPU_SAMPLE)
     for _ in range(max(args.warmup, 1)):
-        cpu_step(x)
+        cpu_step(x, fn)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(x)
+        cpu_step(x, fn)
     dt = time.perf_counter() - t0
     value = CPU_SAMPLE * args.steps / dt / 1e9
-    sample = (f'1 channel x {CPU_SAMPLE} samples per step ({CPU_SAMPLE / FS:.3f} s of the 10 s capture), same '
-              f'nfft/overlap/statistics; numpy/scipy oracle port of the reference, scipy.fft workers = '
-              f'cpu_count//2 = {cpu_cores()} of {os.cpu_count()} cores (the reference policy, fourier.py:214), '
-              f'numpy stages single-threaded as in the reference')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(args.gpus, SAMPLES_PER_CHANNEL),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cpu_cores(), 'kind': 'port',
-                         'sample': sample},
+        'data': 'synthetic',
+        # same `config` as the GPU arm (the workload the metric is quoted on); what one step of THIS arm
+        # really processes is config.cpu_arms_step and the `step_processed` key below
+        'config': workload_config(args.gpus, SAMPLES_PER_CHANNEL),
+        'step_processed': {'channels': 1, 'samples_per_channel': CPU_SAMPLE, 'processes': 1,
+                           'note': 'one CPU process at every N; value = samples processed / wall time'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cpu_cores(), 'kind': kind,
+                         'sample': cpu_sample_note(kind)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -194,6 +228,66 @@ def ncu_traffic(kernel):
         return None
 
 
+def _timed(torch, fn, reps=3):
+    out = fn(); del out
+    torch.cuda.synchronize()
+    best = float('inf')
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(reps):
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1)); del out
+    return best
+
+
+def extra_configs(torch, iqw, dev, peak):
+    """one-shot timings of the other BASELINE.json configs on one GPU: device-resident synthetic input
+    larger than L2, CUDA events on the launching stream, best of 3 after one warm-up call"""
+    rows = []
+
+    def row(name, n, ms, bps):
+        gbs = n * bps / ms / 1e6
+        rows.append({'config': name, 'samples': n, 'ms': round(ms, 4), 'GS_per_s': round(n / ms / 1e6, 2),
+                     'algorithmic_bytes_per_sample': bps, 'algorithmic_GBps': round(gbs, 1),
+                     'frac_of_measured_hbm_peak': round(gbs / peak, 4)})
+
+    # configs[1]: stft/spectrogram, 100 MS/s x 10 s, nfft 2048 Blackman-Harris, 50 % overlap, dB
+    n = 1_000_000_000
+    x = device_capture(torch, n, 2, dev)
+    kw = dict(fs=100e6, window='blackmanharris', nperseg=2048, noverlap=1024, return_axis_arrays=False)
+    row('configs[1] spectrogram dB, 1e9 samples, nfft 2048 blackmanharris 50 %', n,
+        _timed(torch, lambda: iqw.spectrogram(x, dB=True, **kw)), 16)
+    row('configs[1] spectrogram power, same capture', n, _timed(torch, lambda: iqw.spectrogram(x, **kw)), 16)
+    # configs[2] with reducible statistics only: no spectrogram is materialised (8 B/sample compulsory)
+    kw3 = dict(fs=FS, window=WINDOW, resolution=FS / NFFT, fractional_overlap=OVERLAP, dB=True, axis=1)
+    row('configs[2] persistence_spectrum statistics=[mean, max] (fused, nothing materialised)', n,
+        _timed(torch, lambda: iqw.persistence_spectrum(x.view(1, n), statistics=['mean', 'max'], **kw3)), 8)
+    del x
+    torch.cuda.empty_cache()
+    # configs[3]: iq_to_bin_power, 1 ms bins at 245.76 MS/s; the 30 s half-capture one GPU of a pair holds
+    n = 245_760 * 30_000
+    x = torch.empty(n, dtype=torch.complex64, device=dev)
+    xr = torch.view_as_real(x)
+    for s0 in range(0, n, 1 << 28):
+        xr[s0:s0 + (1 << 28)].normal_(0.0, 0.7)
+    for kind in ('mean', 'peak'):
+        row(f'configs[3] iq_to_bin_power {kind}, 1 ms bins, 245.76 MS/s x 30 s (59 GB)', n,
+            _timed(torch, lambda: iqw.iq_to_bin_power(x, 1 / 245.76e6, 1e-3, kind=kind)), 8)
+    del x, xr
+    torch.cuda.empty_cache()
+    # configs[4]: nfft sweep at 50 % and 75 % overlap
+    n = 1 << 28
+    x = torch.randn(n, dtype=torch.complex64, device=dev)
+    for nfft in (64, 256, 1024, 8192, 65536):
+        for ov in (0.5, 0.75):
+            nov = int(nfft * ov)
+            row(f'configs[4] spectrogram nfft {nfft} overlap {ov:.2f}', n,
+                _timed(torch, lambda: iqw.spectrogram(x, fs=1e8, window='hann', nperseg=nfft, noverlap=nov,
+                                                      return_axis_arrays=False)), 8 + 4 * nfft / (nfft - nov))
+    del x
+    torch.cuda.empty_cache()
+    return rows
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -221,10 +315,12 @@ def run_b200(args):
     kw = dict(fs=FS, window=WINDOW, resolution=FS / NFFT, fractional_overlap=OVERLAP,
               statistics=STATS, dB=True, axis=1)
 
+    gathered = {}
+
     def step(inp):
         out = iqw.persistence_spectrum(inp, **kw)
         if world > 1:       # the (4, 4096) rows of every channel on every rank: one NCCL all_gather
-            iqw.distributed.gather_rows(out if out.is_cuda else out.to(dev))
+            gathered['rows'] = iqw.distributed.gather_rows(out if out.is_cuda else out.to(dev))
         return out
 
     def barrier():
@@ -257,6 +353,18 @@ def run_b200(args):
     ms = float(t.item())
     value = world * n * args.steps / (ms * 1e-3) / 1e9
 
+    # ---- N > 1: the gathered rows of a FOREIGN channel equal rank 0's own computation of that channel --
+    shard_parity = None
+    if world > 1:
+        rows = gathered['rows'].clone()                 # (world, 4, 4096) of the last timed step
+        if rank == 0:
+            other = world - 1                           # the capture of the last rank, regenerated from its seed
+            xf = device_capture(torch, n, 1234 + 1000 * other, dev).view(1, n)
+            mine = iqw.persistence_spectrum(xf, **kw)
+            shard_parity = bool(torch.equal(mine[0], rows[other])) and bool(torch.isfinite(rows).all())
+            del xf, mine
+        barrier()
+
     # ---- end to end: pinned host input, result read back ---------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -274,11 +382,31 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        # the ceiling of this metric: the same pinned buffer copied to the device and nothing else, every
+        # rank at the same time (shared PCIe uplinks / host memory included), same barrier bracket
+        dst = torch.empty((1, n), dtype=torch.complex64, device=dev)
+        dst.copy_(host, non_blocking=True)
+        barrier()
+        c0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(host, non_blocking=True)
+        barrier()
+        dc = (time.perf_counter() - c0) / 3
+        t = torch.tensor([dc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dc = float(t.item())
+        del dst
         e2e = {'value': world * n * args.steps / dt / 1e9, 'unit': UNIT,
                'h2d_bytes_per_step': world * n * 8,
                'd2h_bytes_per_step': world * res.numel() * 4,
                'ms_per_step': dt / args.steps * 1e3,
                'api': 'iqwaveform_b200.persistence_spectrum(pinned CPU torch tensor) -> CPU tensor',
+               'h2d_ceiling': {'value': world * n / dc / 1e9, 'unit': UNIT, 'ms_per_step': dc * 1e3,
+                               'GBps_per_gpu': n * 8 / dc / 1e9,
+                               'what': 'measured here: pure pinned host->device copy of the same buffers, all '
+                                       'ranks at once, max over ranks, mean of 3'},
+               'frac_of_h2d_ceiling': round((dc * args.steps) / dt, 4),
                'host_cpus_rank0': numa_cpus}
         del host
 
@@ -311,22 +439,29 @@ def run_b200(args):
                 'algorithmic_bytes_per_launch': alg_bytes[top['kernel']],
                 'avg_launch_ms': top['avg_ms'], 'share_of_step': top['share'],
                 # whole pipeline against the two lower bounds of SURVEY.md 8d
-                'pipeline_materialise_once_frac': round(24 * value / peak, 4),
-                'pipeline_compulsory_frac': round(8 * value / peak, 4),
+                # (per GPU: the aggregate value divided by the number of GPUs, each against one GPU's peak)
+                'pipeline_materialise_once_frac': round(24 * value / world / peak, 4),
+                'pipeline_compulsory_frac': round(8 * value / world / peak, 4),
                 'stages': stages}
 
     # ---- CPU baseline on a bounded sample ------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
+        fn, kind = reference_api()
         xc = cpu_capture(CPU_SAMPLE)
-        cpu_step(xc)
+        cpu_step(xc, fn)
         best = float('inf')
         for _ in range(2):
-            t0 = time.perf_counter(); cpu_step(xc); best = min(best, time.perf_counter() - t0)
-        cpu = {'value': CPU_SAMPLE / best / 1e9, 'unit': UNIT, 'cores': cpu_cores(), 'kind': 'port',
-               'sample': f'1 channel x {CPU_SAMPLE} samples ({CPU_SAMPLE / FS:.3f} s of capture), same '
-                         f'nfft/overlap/statistics, best of 2 after 1 warm-up; oracle port = the reference\'s '
-                         f'own scipy.fft (workers=cpu_count//2={cpu_cores()} of {os.cpu_count()}) + np.quantile calls'}
+            t0 = time.perf_counter(); cpu_step(xc, fn); best = min(best, time.perf_counter() - t0)
+        cpu = {'value': CPU_SAMPLE / best / 1e9, 'unit': UNIT, 'cores': cpu_cores(), 'kind': kind,
+               'sample': cpu_sample_note(kind) + '; best of 2 after 1 warm-up'}
+
+    # ---- the other BASELINE configs, one-shot (N = 1 only) -----------------------------------------
+    extra = None
+    if world == 1 and not args.no_extra:
+        del x
+        torch.cuda.empty_cache()
+        extra = {'configs': extra_configs(torch, iqw, dev, peak)}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -335,6 +470,13 @@ def run_b200(args):
         'config': workload_config(world, n), 'clocks': clocks, 'e2e': e2e,
         'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'impl': 'b200',
     }
+    if shard_parity is not None:
+        line['shard_parity'] = shard_parity
+        line['shard_parity_what'] = ('rank 0 regenerated the last rank\'s capture from its seed, ran the '
+                                     'persistence spectrum locally and compared it bit for bit (torch.equal) '
+                                     'with that channel\'s rows of the NCCL all_gather')
+    if extra is not None:
+        line['extra'] = extra
     if world > 1:
         dist.destroy_process_group()
     return line
@@ -367,6 +509,7 @@ def main():
                     help='samples per channel (default: the full 10 s capture)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the one-shot timings of the other configs')
     args = ap.parse_args()
     if args.impl == 'reference':
         with QuietStdout():

@@ -34,8 +34,12 @@ struct ProfRec { const char* name; int launches; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 
 int profile_level() { return g_prof_level.load(std::memory_order_relaxed); }
+// at most kProfCap open records: a caller that leaves profiling on without ever reading the report
+// gets the oldest scopes only, and the events of the dropped ones are released at once
+static constexpr size_t kProfCap = 1 << 16;
 void profile_push(const char* name, int launches, cudaEvent_t a, cudaEvent_t b) {
     std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (g_prof.size() >= kProfCap) { cudaEventDestroy(a); cudaEventDestroy(b); return; }
     g_prof.push_back({name, launches, a, b});
 }
 

@@ -185,6 +185,7 @@ extern "C" int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_
                                  int64_t bin_len, int64_t n_bins, float* d_mean, float* d_max,
                                  float* d_min, void* d_workspace, size_t workspace_bytes,
                                  void* stream) {
+    iqw::DeviceGuard _dev_guard(d_x);
     if (!d_x) return fail(IQW_ERR_INVALID, "null input");
     if (!d_mean && !d_max && !d_min) return fail(IQW_ERR_INVALID, "no output requested");
     if (bin_len < 1 || n_bins < 0 || n_channels < 0) return fail(IQW_ERR_INVALID, "bad sizes");
@@ -247,6 +248,7 @@ extern "C" int iqw_bin_power_c64(const void* d_x, int64_t n_channels, int64_t x_
 extern "C" int iqw_envtopow_transposed_c64(const void* d_x, int64_t n_channels,
                                            int64_t x_channel_stride, int64_t bin_len,
                                            int64_t n_bins, float* d_out, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_x);
     if (!d_x || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (bin_len < 1 || n_bins < 0 || n_channels < 0) return fail(IQW_ERR_INVALID, "bad sizes");
     if (n_bins == 0 || n_channels == 0) return IQW_OK;

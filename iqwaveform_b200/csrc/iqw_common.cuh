@@ -28,6 +28,26 @@ inline int fail(int code, const char* fmt, ...) {
 
 int device_sm_count(int* sms);
 
+// Every compute entry point launches on the device that OWNS its buffers, whatever device is current
+// in the calling thread (a tensor on cuda:1 while cuda:0 is current would otherwise be launched on the
+// wrong device, with a foreign stream and a twiddle table of the other device).  The previous device
+// is restored on return.  Costs one cudaPointerGetAttributes (~0.3 us) per call.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const void* p) {
+        if (!p) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+        if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (at.device != prev && cudaSetDevice(at.device) == cudaSuccess) switched = true;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // Optional kernel timing (off by default): a launch site is wrapped in a scope that records a CUDA
 // event before and after it ON THE LAUNCHING STREAM.  Level 1 (what bench.py runs its timed region
 // under) times the heavy kernels one by one and the trains of small follow-up kernels as one scope

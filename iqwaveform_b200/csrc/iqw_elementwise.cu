@@ -95,6 +95,7 @@ using namespace iqw;
 
 extern "C" int iqw_elementwise_f32(int32_t op, const float* d_in, float* d_out, int64_t n, int32_t use_abs,
                                    float eps, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_in);
     if (n < 0) return fail(IQW_ERR_INVALID, "negative size");
     if (n == 0) return IQW_OK;
     if (!d_in || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
@@ -121,6 +122,7 @@ extern "C" int iqw_elementwise_f32(int32_t op, const float* d_in, float* d_out, 
 }
 
 extern "C" int iqw_elementwise_c64(int32_t op, const void* d_in, float* d_out, int64_t n, float eps, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_in);
     if (n < 0) return fail(IQW_ERR_INVALID, "negative size");
     if (n == 0) return IQW_OK;
     if (!d_in || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");

@@ -106,6 +106,7 @@ using namespace iqw;
 
 extern "C" int iqw_edge_counts_f32(const float* d_a, int64_t n_rows, int64_t n_cols, const double* d_edges,
                                    int32_t n_edges, int32_t side_right, int64_t* d_counts, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_a);
     if (!d_a || !d_edges || !d_counts || n_rows < 1 || n_cols < 1 || n_edges < 1)
         return fail(IQW_ERR_INVALID, "iqw_edge_counts_f32: bad argument");
     if (n_edges > kHiMaxEdges)

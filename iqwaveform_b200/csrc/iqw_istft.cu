@@ -414,6 +414,7 @@ extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_fram
                              int32_t nfft, int64_t hop, int32_t bin_lo, int32_t bin_hi, int32_t y_bins,
                              const void* d_bin_gain, float scale, void* d_out, int64_t out_channel_stride,
                              void* stream) {
+    iqw::DeviceGuard _dev_guard(d_y);
     return istft_entry(d_y, n_channels, n_frames, y_channel_stride, nfft, hop, bin_lo, bin_hi, y_bins,
                        d_bin_gain, scale, 0, d_out, out_channel_stride, stream);
 }
@@ -421,6 +422,7 @@ extern "C" int iqw_istft_c64(const void* d_y, int64_t n_channels, int64_t n_fram
 // plain batched inverse DFT (1/nfft normalised, natural bin order in, natural sample order out):
 // kernel 4 with hop = nfft (nothing to overlap-add) and without the (-1)^n of the baked-in shift
 extern "C" int iqw_ifft_c64(const void* d_y, int64_t n_rows, int32_t nfft, void* d_out, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_y);
     if (n_rows < 1) return fail(IQW_ERR_INVALID, "ifft: need at least one row");
     return istft_entry(d_y, 1, n_rows, n_rows * (int64_t)nfft, nfft, nfft, 0, nfft, nfft, nullptr, 1.0f, 1,
                        d_out, n_rows * (int64_t)nfft, stream);
@@ -430,6 +432,7 @@ extern "C" int iqw_ola_filter_c64(const void* d_x, int64_t n_channels, int64_t n
                                   const float* d_window, int32_t nfft, int64_t hop, int64_t n_frames,
                                   int32_t bin_lo, int32_t bin_hi, void* d_out, int64_t out_channel_stride,
                                   void* stream) {
+    iqw::DeviceGuard _dev_guard(d_x);
     if (!d_x || !d_out || !d_window) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (nfft < 2 || (nfft & (nfft - 1)))
         return fail(IQW_ERR_UNSUPPORTED, "nfft=%d: only powers of two are built", nfft);

@@ -300,6 +300,7 @@ static int launch_count(const float* d_p, int64_t n_rows, int64_t n_cols, int n_
 extern "C" int iqw_radix_count_f32(const float* d_p, int64_t n_rows, int64_t n_cols, int32_t n_sel,
                                    const uint32_t* d_lo, const uint32_t* d_hi, int32_t level,
                                    int32_t* d_counts, int32_t* d_below, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_lo);
     if (n_rows < 0 || n_cols < 1 || n_sel < 1 || level < 0 || level > 3 || !d_counts || !d_lo || !d_hi ||
         (n_rows > 0 && !d_p))
         return fail(IQW_ERR_INVALID, "iqw_radix_count_f32: bad argument");
@@ -353,6 +354,7 @@ static CollectView collect_view(void* ws, int64_t n_rows, int64_t n_cols) {
 extern "C" int iqw_bracket_collect_f32(const float* d_p, int64_t n_rows, int64_t n_cols, int32_t n_sel,
                                        const uint32_t* d_lo, const uint32_t* d_hi, int32_t* d_below,
                                        void* d_workspace, size_t workspace_bytes, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_lo);
     if (n_rows < 0 || n_cols < 1 || n_sel < 1 || n_sel > kRsMaxSel || !d_lo || !d_hi || !d_below || (n_rows > 0 && !d_p))
         return fail(IQW_ERR_INVALID, "iqw_bracket_collect_f32: bad argument (1 <= n_sel <= %d)", kRsMaxSel);
     if (n_rows >= (int64_t)1 << 31) return fail(IQW_ERR_UNSUPPORTED, "iqw_bracket_collect_f32: more than 2^31-1 rows");
@@ -375,6 +377,7 @@ extern "C" int iqw_bracket_collect_f32(const float* d_p, int64_t n_rows, int64_t
 extern "C" int iqw_candidate_count_f32(const void* d_workspace, int64_t n_rows, int64_t n_cols, int32_t n_sel,
                                        const uint32_t* d_lo, const uint32_t* d_hi, int32_t level,
                                        int32_t* d_counts, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_workspace);
     if (n_rows < 0 || n_cols < 1 || n_sel < 1 || n_sel > kRsMaxSel || level < 0 || level > 3 || !d_counts || !d_lo ||
         !d_hi || (n_rows > 0 && !d_workspace))
         return fail(IQW_ERR_INVALID, "iqw_candidate_count_f32: bad argument");
@@ -399,6 +402,7 @@ extern "C" int iqw_candidate_count_f32(const void* d_workspace, int64_t n_rows, 
 extern "C" int iqw_radix_descend(const int32_t* d_counts, int32_t n_sel, int64_t n_cols, int32_t level,
                                  int64_t* d_rank, uint32_t* d_prefix, uint32_t* d_lo, uint32_t* d_hi,
                                  void* stream) {
+    iqw::DeviceGuard _dev_guard(d_counts);
     if (!d_counts || !d_rank || !d_prefix || !d_lo || !d_hi || n_sel < 1 || n_cols < 1 || level < 0 || level > 3)
         return fail(IQW_ERR_INVALID, "iqw_radix_descend: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
@@ -413,6 +417,7 @@ extern "C" int iqw_radix_descend(const int32_t* d_counts, int32_t n_sel, int64_t
 extern "C" int iqw_order_stats_finish_f32(const uint32_t* d_keys, int32_t n_sel, const int64_t* sel_rank,
                                           int64_t n_rows_total, int64_t n_cols, const iqw_stat* stats,
                                           int32_t n_stats, int32_t to_dB, float eps, float* d_out, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_keys);
     if (!d_keys || !sel_rank || !stats || !d_out || n_sel < 1 || n_cols < 1 || n_stats < 1 || n_stats > kRsMaxStats)
         return fail(IQW_ERR_INVALID, "iqw_order_stats_finish_f32: bad argument");
     FinishPlan fp;

@@ -45,6 +45,7 @@
 // Keys are the order-preserving uint32 image of the float (iqw_common.cuh float_to_key), so the
 // selection is exact for any input, ties and signed zeros included.  NaNs sort above +inf.
 #include <cmath>
+#include <atomic>
 #include "iqw_common.cuh"
 
 namespace iqw {
@@ -1410,8 +1411,8 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
 
 // long-column plan: row splits of the bracket pass, the row sample, and per group of target
 // ranks the two SAMPLE ranks (margin-sigma away) whose keys bracket it.
-static double g_margin_sigmas = 5.0;   // iqw_debug_set_sample_margin; 5 sigma: ~1 % of config-3 calls refine one column
-static int g_margin_extra = 2;
+static std::atomic<double> g_margin_sigmas{5.0};   // iqw_debug_set_sample_margin; 5 sigma: ~1 % of config-3 calls refine one column
+static std::atomic<int> g_margin_extra{2};
 
 struct LongPlan {
     long long splits, rows_per_split;
@@ -1454,7 +1455,7 @@ static bool build_long_plan(const RankPlan& rp, int64_t rows, int64_t cols, int 
     const double f = (double)srows / (double)rows;
     auto margin = [&](double r) {
         const double q = r / (double)rows;
-        return (int64_t)std::ceil(g_margin_sigmas * std::sqrt((double)srows * q * (1.0 - q))) + g_margin_extra;
+        return (int64_t)std::ceil(g_margin_sigmas.load() * std::sqrt((double)srows * q * (1.0 - q))) + g_margin_extra.load();
     };
     int64_t lo[kMaxRanks], hi[kMaxRanks];
     int ng = 0;
@@ -1675,6 +1676,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
                                   int64_t n_cols, int64_t p_channel_stride, const iqw_stat* stats,
                                   int32_t n_stats, int32_t to_dB, float eps, float* d_out,
                                   void* d_workspace, size_t workspace_bytes, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_p);
     if (!d_p || !stats || !d_out || !d_workspace) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (n_stats < 1 || n_stats > kMaxStats)
         return fail(IQW_ERR_INVALID, "n_stats=%d outside 1..%d", n_stats, kMaxStats);

@@ -203,6 +203,7 @@ extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_sampl
                             int64_t hop, int64_t n_frames, int32_t mode, float eps, int32_t bin_lo,
                             int32_t bin_hi, void* d_out, int64_t out_channel_stride, void* d_workspace,
                             size_t workspace_bytes, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_x);
     if (!d_x || !d_window || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
     if (nfft < 2 || (nfft & (nfft - 1)))
         return fail(IQW_ERR_UNSUPPORTED, "nfft=%d: only powers of two are built", nfft);

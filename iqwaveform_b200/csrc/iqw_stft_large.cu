@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <mutex>
 #include <map>
+#include <atomic>
 #include "iqw_stft.cuh"
 
 namespace iqw {
@@ -27,7 +28,7 @@ namespace iqw {
 constexpr int kLog2N2 = 8;
 constexpr int kN2 = 1 << kLog2N2;
 constexpr int kCols = 16;                         // n2 per CTA of columns_kernel / k1 per CTA of rows_kernel
-static size_t g_scratch_cap = 1ull << 30;         // bytes of scratch per chunk of frames (iqw_debug_set_stft_scratch_cap)
+static std::atomic<size_t> g_scratch_cap{1ull << 30};         // bytes of scratch per chunk of frames (iqw_debug_set_stft_scratch_cap)
 
 struct LargeArgs {
     StftArgs a;
@@ -304,7 +305,8 @@ size_t stft_large_workspace_bytes(int log2n, long long n_channels, long long n_f
     if (log2n < 14 || log2n > 16 || n_channels < 1 || n_frames < 1) return 0;
     const size_t frame_bytes = sizeof(float2) << log2n;
     const size_t all = frame_bytes * (size_t)n_channels * (size_t)n_frames;
-    const size_t cap = g_scratch_cap / frame_bytes * frame_bytes > 0 ? g_scratch_cap / frame_bytes * frame_bytes : frame_bytes;
+    const size_t cap_bytes = g_scratch_cap.load();
+    const size_t cap = cap_bytes / frame_bytes * frame_bytes > 0 ? cap_bytes / frame_bytes * frame_bytes : frame_bytes;
     return all < cap ? all : cap;
 }
 

@@ -202,15 +202,20 @@ def persistence_spectrum_sharded(x_local, *, n_channels: int, group=None, comput
     if compute is None:
         from .fourier import persistence_spectrum as compute
     world, rank = _world(group)
+    # every rank derives this from the arguments alone, so all of them raise together: a raise on a
+    # subset of the ranks ahead of the all_gather would leave the others blocked in the collective
+    if n_channels < 1:
+        raise ValueError('n_channels must be >= 1')
+    if world > n_channels:
+        raise ValueError(f'{world} ranks for {n_channels} channels: every rank needs at least one channel '
+                         f'(run the call on a sub-group of {n_channels} ranks)')
     mine = channel_shard(n_channels, world, rank)
     if x_local.shape[0] != len(mine):
         raise ValueError(f'rank {rank} expects {len(mine)} channels, got {x_local.shape[0]}')
     kw = dict(kw, axis=1)
-    out = compute(x_local, **kw) if len(mine) else None
+    out = compute(x_local, **kw)
     if world == 1:
         return out
-    if out is None:     # more ranks than channels: contribute an empty shard of the right row shape
-        raise ValueError('every rank needs at least one channel (use a sub-group otherwise)')
     out = torch.as_tensor(out)
     return gather_rows(out, [len(channel_shard(n_channels, world, r)) for r in range(world)], 0, group)
 

@@ -9,8 +9,13 @@ smallest set of stand-ins that lets ``import iqwaveform`` run WITHOUT editing re
 * ``xarray``/``methodtools``-> empty stand-ins (never touched on the hot path)
 * ``scipy.signal.windows._windows._win_equiv`` -> ``{}`` when missing (``windows.py:119``)
 
-``/root/reference`` exists only in the build container; ``load()`` returns ``None`` elsewhere and
-nothing that runs on the GPU box may depend on it.
+``/root/reference`` exists only in the build container.  ``__graft_entry__.build()`` therefore copies the
+reference's package directory, byte for byte, to the git-ignored ``baseline/_ref/iqwaveform`` (the
+contract's install target; ``pip install --target`` itself fails here because the reference's build
+backend, hatchling, is not in the image -- the package is pure Python, so the copy IS the install).
+That copy travels to the GPU box with the repo snapshot and is what ``bench.py --impl reference``
+times there.  ``load()`` prefers ``/root/reference/src`` and falls back to ``baseline/_ref``; it
+returns ``None`` when neither exists.
 """
 from __future__ import annotations
 
@@ -20,11 +25,36 @@ import os
 import sys
 import types
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFERENCE_SRC = '/root/reference/src'
+INSTALLED_SRC = os.path.join(_ROOT, 'baseline', '_ref')
+
+
+def source_dir() -> str | None:
+    """directory holding the unmodified reference package: the read-only checkout in the build
+    container, else the copy `build()` installed under baseline/_ref"""
+    for d in (REFERENCE_SRC, INSTALLED_SRC):
+        if os.path.isfile(os.path.join(d, 'iqwaveform', 'fourier.py')):
+            return d
+    return None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, 'iqwaveform'))
+    return source_dir() is not None
+
+
+def install() -> str | None:
+    """copy the reference package to baseline/_ref (build container only); returns the target or None"""
+    import shutil
+    src = os.path.join(REFERENCE_SRC, 'iqwaveform')
+    if not os.path.isdir(src):
+        return None
+    dst = os.path.join(INSTALLED_SRC, 'iqwaveform')
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    os.makedirs(INSTALLED_SRC, exist_ok=True)
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns('__pycache__'))
+    return dst
 
 
 def _stub(name: str, **attrs):
@@ -71,6 +101,7 @@ def load():
     if not hasattr(_w, '_win_equiv'):
         _w._win_equiv = {}
 
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    src = source_dir()
+    if src not in sys.path:
+        sys.path.insert(0, src)
     return importlib.import_module('iqwaveform')

@@ -66,3 +66,23 @@ def test_sharded_equals_single_gpu_nccl(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+def test_tensor_on_non_current_device(cuda_device):
+    """every C entry point launches on the device that owns its buffers: a capture on cuda:1 while
+    cuda:0 is the current device gives the same bits as the same capture on cuda:0"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs at least 2 GPUs')
+    import iqwaveform_b200 as iqw
+    from oracle.make_golden import synth
+    x = synth(3, (2, 1 << 17))
+    kw = dict(fs=1e6, window='hann', resolution=1e6 / 1024, fractional_overlap=0.5,
+              statistics=[0.1, 0.5, 'max', 'mean'], dB=True, axis=1)
+    torch.cuda.set_device(0)
+    a = iqw.persistence_spectrum(torch.from_numpy(x).to('cuda:0'), **kw)
+    b = iqw.persistence_spectrum(torch.from_numpy(x).to('cuda:1'), **kw)       # cuda:0 still current
+    assert torch.cuda.current_device() == 0 and b.device.index == 1
+    assert torch.equal(a.cpu(), b.cpu())
+    pa = iqw.iq_to_bin_power(torch.from_numpy(x).to('cuda:0'), 1e-6, 1e-3, kind='peak', axis=1, truncate=True)
+    pb = iqw.iq_to_bin_power(torch.from_numpy(x).to('cuda:1'), 1e-6, 1e-3, kind='peak', axis=1, truncate=True)
+    assert torch.equal(pa.cpu(), pb.cpu())

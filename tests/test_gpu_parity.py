@@ -220,8 +220,49 @@ def test_persistence_vs_golden(cuda_device, name):
                        pw.max(axis=(1, 2))[:, None])
 
 
+def test_persistence_config0_full_size_vs_oracle(cuda_device):
+    """BASELINE configs[0] at FULL size against the oracle (fourier.py:1236-1327): 1 s of complex64
+    noise + tones at 15.36 MS/s, nfft 1024 Hann, 50 % overlap, q = [0.5, 0.99], dB.  T = 29 999 frames:
+    the long-column path of kernel 2 (row sample -> brackets -> one read of the matrix) on real STFT
+    data.  About 2 s of CPU for the oracle."""
+    n = 15_360_000
+    x = synth(77, (1, n))
+    args = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5,
+                statistics=[0.5, 0.99], dB=True, axis=1)
+    ref = orc.persistence_spectrum(x, **args)
+    got = iqw.persistence_spectrum(dev_of(x, cuda_device), **args)
+    assert tuple(got.shape) == ref.shape == (1, 2, 1024)
+    _, _, p = orc.spectrogram(x, fs=15.36e6, window='hann', nperseg=1024, noverlap=512, axis=1)
+    assert p.shape[1] == 29999
+    _check_persistence(got.cpu().numpy(), ref, [0.5, 0.99], x, 1024, True, p.max(axis=(1, 2))[:, None])
+    # the selection is exact: on the device's own spectrogram the rows are bitwise numpy's quantiles
+    pd = iqw.spectrogram(dev_of(x, cuda_device), fs=15.36e6, window='hann', nperseg=1024, noverlap=512,
+                         axis=1, return_axis_arrays=False)
+    cnt = []
+    sel = iqw.time_statistics(pd, [0.5, 0.99], dB=False, counters=cnt).cpu().numpy()
+    want = np.quantile(pd.cpu().numpy(), np.array([0.5, 0.99], dtype=np.float32), axis=1)
+    assert np.array_equal(sel, np.moveaxis(want, 0, 1))
+    assert cnt[0]['inconsistent'] == 0
+
+
+def test_persistence_long_path_two_channels_vs_oracle(cuda_device):
+    """(2, 2^23) samples, nfft 1024, 50 % overlap: T = 16 383 -> the long-column path, with mean, max and
+    four quantiles, two channels (the two-stream channel pipeline is not taken at this size)"""
+    n, nfft = 1 << 23, 1024
+    x = synth(5, (2, n))
+    stats = ['mean', 'max', 0.1, 0.5, 0.9, 0.999]
+    args = dict(fs=1e6, window='hann', resolution=1e6 / nfft, fractional_overlap=0.5, statistics=stats,
+                dB=True, axis=1)
+    ref = orc.persistence_spectrum(x, **args)
+    got = iqw.persistence_spectrum(dev_of(x, cuda_device), **args)
+    assert tuple(got.shape) == ref.shape == (2, 6, nfft)
+    _, _, p = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nfft // 2, axis=1)
+    assert p.shape[1] == 16383
+    _check_persistence(got.cpu().numpy(), ref, stats, x, nfft, True, p.max(axis=(1, 2))[:, None])
+
+
 def test_persistence_1d_and_config1_shape(cuda_device):
-    """BASELINE config 1 at reduced length (the full 1 s runs in bench.py)"""
+    """BASELINE config 1 at a tenth of its length, 1-D input (the full size is the test above)"""
     x = synth(21, (1, 1536000))
     args = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5,
                 statistics=[0.5, 0.99], dB=True)
