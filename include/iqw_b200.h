@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IQW_ABI_VERSION 7
+#define IQW_ABI_VERSION 8
 
 typedef enum iqw_status {
     IQW_OK = 0,
@@ -270,6 +270,13 @@ int iqw_order_stats_finish_f32(const uint32_t* d_keys, int32_t n_sel, const int6
 /* Tuning aid: bytes of scratch iqw_stft_workspace_bytes asks for (nfft > 8192); frames are
  * processed in chunks of that size. */
 int iqw_debug_set_stft_scratch_cap(size_t bytes);
+
+/* Tuning aid: which kernel-1 geometry serves nfft 1024 / 2048 / 4096.  0 = automatic (the two-pass
+ * kernel, csrc/iqw_stft2p.cu: 32 / 64 values per thread, one shared-memory exchange per frame, frames
+ * staged by bulk copies (TMA) when every frame start is 16-byte aligned), 1 = always the three-pass kernel
+ * (csrc/iqw_stft.cu: 16 values per thread, two exchanges), 2 = two-pass with plain global loads, 3 = two-pass
+ * staged (same as 0).  All compute the same transform; results differ by float32 rounding only. */
+int iqw_debug_set_stft_variant(int variant);
 
 /* Test aid: width of the brackets the row sample puts around each target rank on the long-column
  * path of iqw_time_stats_f32 (default 5 sigma + 2 ranks).  Results are exact for ANY setting -- a

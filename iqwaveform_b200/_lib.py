@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libiqw_b200.so')
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # statuses / enums mirrored from include/iqw_b200.h
 IQW_OK = 0
@@ -68,6 +68,7 @@ SIGNATURES = {
     'iqw_order_stats_finish_f32': (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i64), _i64, _i64,
                                                   ctypes.POINTER(iqw_stat), _i32, _i32, _f32, _vp, _vp]),
     'iqw_debug_set_stft_scratch_cap': (ctypes.c_int, [_sz]),
+    'iqw_debug_set_stft_variant': (ctypes.c_int, [ctypes.c_int]),
     'iqw_debug_set_sample_margin': (ctypes.c_int, [ctypes.c_double, ctypes.c_int]),
     'iqw_debug_time_stats_counters': (ctypes.c_int, [_vp, _i64, ctypes.POINTER(ctypes.c_uint32)]),
     'iqw_profile_enable': (ctypes.c_int, [ctypes.c_int]),

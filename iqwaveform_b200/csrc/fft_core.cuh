@@ -306,4 +306,75 @@ IQW_HD void fft_pass(float2* v, const float2* src, float2* dst, const float2* t,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// radix-32 / radix-64 in-register DFTs for the two-pass kernels (iqw_stft2p.cu): 8 x 4 and 8 x 8
+// decompositions over bfly4 / bfly8 with compile-time W64 constants.  All indices are compile-time
+// after unrolling, so the 64 values stay in registers.
+// ------------------------------------------------------------------------------------------
+IQW_HD constexpr float cos64_q(int m) {      // cos(2 pi m / 64), 0 <= m <= 16
+    switch (m) {
+        case 0: return 1.0f; case 1: return 9.951847267e-01f; case 2: return 9.807852804e-01f; case 3: return 9.569403357e-01f; case 4: return 9.238795325e-01f; case 5: return 8.819212643e-01f; case 6: return 8.314696123e-01f; case 7: return 7.730104534e-01f; case 8: return 7.071067812e-01f; case 9: return 6.343932842e-01f; case 10: return 5.555702330e-01f; case 11: return 4.713967368e-01f; case 12: return 3.826834324e-01f; case 13: return 2.902846773e-01f; case 14: return 1.950903220e-01f; case 15: return 9.801714033e-02f; case 16: return 0.0f;
+    }
+    return 0.0f;
+}
+IQW_HD constexpr float cos64(int m) {
+    m &= 63;
+    if (m > 32) m = 64 - m;
+    return m > 16 ? -cos64_q(32 - m) : cos64_q(m);
+}
+IQW_HD constexpr float sin64(int m) { return cos64((m + 48) & 63); }
+
+// a * W64^m = a * exp(-2 pi i m / 64), m a compile-time constant after unrolling
+IQW_HD float2 mul_w64(float2 a, int m) {
+    m &= 63;
+    if (m == 0) return a;
+    if (m == 16) return mul_mi(a);
+    if (m == 32) return make_float2(-a.x, -a.y);
+    if (m == 48) return make_float2(-a.y, a.x);
+    if (m == 8) return mul_w8_1(a);
+    if (m == 24) return mul_w8_3(a);
+    return cmul(a, make_float2(cos64(m), -sin64(m)));
+}
+
+// 64-point forward DFT in place, natural order in and out.  r = 8a + b, k = c + 8d:
+// W64^(rk) = W8^(ac) W64^(bc) W8^(bd)
+IQW_HD void bfly64(float2* a) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) bfly8<8>(a + b);                 // a[8c + b] = y[b][c]
+#pragma unroll
+    for (int b = 1; b < 8; ++b)
+#pragma unroll
+        for (int c = 1; c < 8; ++c) a[8 * c + b] = mul_w64(a[8 * c + b], b * c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bfly8<1>(a + 8 * c);             // a[8c + d] = X[c + 8d]
+    float2 t[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) t[k] = a[8 * (k & 7) + (k >> 3)];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a[k] = t[k];
+}
+
+// 32-point forward DFT in place.  r = 8a + b (a < 4), k = c + 4d (c < 4): W32^(rk) = W4^(ac) W32^(bc) W8^(bd)
+IQW_HD void bfly32(float2* a) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) bfly4<8>(a + b);                 // a[8c + b] = y[b][c], c < 4
+#pragma unroll
+    for (int b = 1; b < 8; ++b)
+#pragma unroll
+        for (int c = 1; c < 4; ++c) a[8 * c + b] = mul_w64(a[8 * c + b], 2 * b * c);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bfly8<1>(a + 8 * c);             // a[8c + d] = X[c + 4d]
+    float2 t[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t[k] = a[8 * (k & 3) + (k >> 2)];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a[k] = t[k];
+}
+
+template <int R>
+IQW_HD void bfly_big(float2* a) {
+    if constexpr (R == 64) bfly64(a);
+    else bfly32(a);
+}
+
 }  // namespace iqw

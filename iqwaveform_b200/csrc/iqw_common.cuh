@@ -97,6 +97,19 @@ __host__ __device__ __forceinline__ float key_to_float(uint32_t k) {
 // log10f so that -inf / nan come out exactly as the reference's.
 static __device__ __noinline__ float power_to_dB_slow(float v) { return 10.0f * log10f(v); }
 
+// the two halves of power_to_dB for kernels that convert many values per thread: a branch-free fast
+// path that is right whenever dB_fast_ok(v), so that the (rare) other arguments can be patched later
+__device__ __forceinline__ bool dB_fast_ok(float v) { return __float_as_uint(v) - 0x00800000u < 0x7F000000u; }
+__device__ __forceinline__ float power_to_dB_fast(float v /* = |p| + eps */, bool& ok) {
+    const uint32_t b = __float_as_uint(v);
+    ok = b - 0x00800000u < 0x7F000000u;
+    const float e = __uint_as_float(0x4B400000u | (b >> 23)) - 12583039.0f;
+    const float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(m));
+    return (e + l) * 3.01029995663981195f;
+}
+
 __device__ __forceinline__ float power_to_dB(float p, float eps) {
     const float v = fabsf(p) + eps;
     const uint32_t b = __float_as_uint(v);

@@ -240,6 +240,7 @@ extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_sampl
     a.out = d_out;
     a.out_ch_stride = out_channel_stride;
     if (log2n > 13) return launch_stft_large(a, log2n, mode, d_workspace, workspace_bytes, s);
+    if (stft_two_pass_wanted(log2n)) return launch_stft_two_pass(a, log2n, mode, s);
     if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;
 
     switch (log2n) {

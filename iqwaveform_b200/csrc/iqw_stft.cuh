@@ -72,6 +72,10 @@ struct PassLoop {
 // immutable per-(device, log2 n) twiddle table of the in-CTA FFT (built on first use)
 int get_twiddles(int log2n, cudaStream_t stream, const float2** out);
 
+// nfft 1024 / 2048 / 4096, two-pass geometry (iqw_stft2p.cu)
+bool stft_two_pass_wanted(int log2n);
+int launch_stft_two_pass(const StftArgs& a, int log2n, int mode, cudaStream_t stream);
+
 // nfft = 2^14 .. 2^16 (iqw_stft_large.cu)
 size_t stft_large_workspace_bytes(int log2n, long long n_channels, long long n_frames);
 int launch_stft_large(const StftArgs& a, int log2n, int mode, void* workspace, size_t workspace_bytes,

@@ -1,0 +1,352 @@
+// iqw_stft2p.cu -- kernel 1, two-pass variant for nfft 1024 / 2048 / 4096 (the headline sizes).
+//
+// Same contract as stft_kernel (iqw_stft.cu): fused overlapped-frame gather * window -> FFT ->
+// {complex | |X|^2 | dB} -> band trim, replacing fourier.py:568-581 + 1044 + power_analysis.py:254-255 +
+// 199-204 + fourier.py:1295 of the reference in one pass over the samples.
+//
+// Why a second geometry.  With 16 values per thread a 4096-point frame needs three radix-16 passes and
+// TWO exchanges through shared memory; ncu showed that kernel bound by the L1/shared-memory data pipe
+// (73 % busy: 2000 wavefronts per frame, 1590 of them shared-memory exchanges and twiddle reads), not by
+// HBM (42 %).  Here a thread holds 64 values (32 for nfft 1024), N = RA x RB with RA, RB in {32, 64}, so a
+// frame is TWO register-resident radix-32/64 passes and ONE exchange: ~1100 wavefronts per frame.
+//   pass A  butterfly jA = ltid (RB of them): elements x[jA + r*RB], r < RA, windowed; writes row jA of
+//           the RB x RA exchange matrix M (Stockham, Ns = 1) with 128-bit stores
+//   pass B  butterfly jB = ltid + q*TPF (RA of them, E/RB per thread): reads column jB of M, multiplies by
+//           W_N^(r*jB), radix-RB DFT; output r' is bin jB + r'*RA (natural order, coalesced stores)
+// A frame slot is TPF = RB threads: ONE warp for nfft 1024 / 2048 (the exchange needs only __syncwarp), two
+// warps for 4096 (a 64-thread named barrier).  Slots are independent: each walks its own contiguous range
+// of frames, so the overlapped half of consecutive frames is re-read from L2 a few microseconds after its
+// first use.  Rows of M are padded by two elements (a row is an odd number of 16-byte units), which makes
+// both the 128-bit row stores and the 64-bit column loads conflict-free.
+#include <mutex>
+#include <map>
+#include <utility>
+#include <atomic>
+#include "iqw_stft.cuh"
+
+#ifndef IQW_P2_SLOTS12
+#define IQW_P2_SLOTS12 6
+#endif
+#ifndef IQW_P2_SLOTS11
+#define IQW_P2_SLOTS11 12
+#endif
+
+namespace iqw {
+
+template <int LOG2N, bool STAGED = true>
+struct P2Cfg {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int RA = LOG2N >= 11 ? 64 : 32;
+    static constexpr int RB = N / RA;                  // 32 (1024), 32 (2048), 64 (4096)
+    static constexpr int E = RA;                       // values per thread
+    static constexpr int TPF = N / E;                  // threads per frame slot == RB
+    static constexpr int NB = E / RB;                  // pass-B butterflies per thread
+    // frame slots per CTA: 12 warps (168 registers per thread; a warp count that is a multiple of the 4
+    // schedulers) for the staged kernels at nfft 2048 / 4096, 8 warps (up to 255 registers) otherwise
+    static constexpr int SLOTS = LOG2N == 12 ? (STAGED ? IQW_P2_SLOTS12 : 4) : LOG2N == 11 ? (STAGED ? IQW_P2_SLOTS11 : 8) : 8;
+    static constexpr int THREADS = SLOTS * TPF;        // 256 or 384
+    static constexpr int MIN_BLOCKS = LOG2N == 10 ? 2 : 1;
+    static constexpr int ROW = RA + 2;                 // padded row of M, float2 units
+    static constexpr int BUF = RB * ROW;               // one slot's exchange matrix
+    // pass-B twiddles W_N^(r*jB), r = 8a + b, factored as A_a * B_b: rows A_1 .. A_(RB/8-1) = W_N^(8a*jB), then
+    // rows B_1 .. B_7 = W_N^(b*jB), each RA entries long (7 KB at nfft 4096 instead of 32 KB for all RB - 1 rows;
+    // 14 shared-memory loads per butterfly instead of 63, the products are computed)
+    static constexpr int NA8 = RB / 8;
+    static constexpr int TW_ROWS = (NA8 - 1) + 7;
+    static constexpr int TW = TW_ROWS * RA;
+    static constexpr size_t SMEM = sizeof(float2) * ((size_t)TW + (size_t)SLOTS * BUF);
+    static_assert(RA >= RB && RA * RB == N && TPF == RB && TPF % 32 == 0, "geometry");
+    static_assert((ROW * sizeof(float2)) % 16 == 0 && ((ROW * sizeof(float2)) / 16) % 2 == 1, "row padding");
+};
+
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+// ---- mbarrier / bulk-copy (TMA) plumbing, raw PTX ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one contiguous span of global memory -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// STAGED: the frame's samples are staged by ONE bulk copy (TMA) per frame into the slot's exchange buffer
+// while the previous frame's second pass and epilogue run -- the buffer is idle exactly then -- so pass A
+// reads shared memory instead of waiting for HBM / L2 with only two warps per scheduler to hide it.
+template <int LOG2N, int MODE, bool FULLBAND, bool STAGED>
+__global__ void __launch_bounds__(P2Cfg<LOG2N, STAGED>::THREADS, P2Cfg<LOG2N, STAGED>::MIN_BLOCKS)
+stft2p_kernel(const StftArgs a) {
+    using C = P2Cfg<LOG2N, STAGED>;
+    constexpr int RA = C::RA, RB = C::RB, E = C::E, TPF = C::TPF, NB = C::NB, ROW = C::ROW;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[C::SLOTS];
+    for (int i = threadIdx.x; i < C::TW; i += C::THREADS) tw[i] = a.twiddle[i];
+    if constexpr (STAGED) {
+        if (threadIdx.x < C::SLOTS) mbar_init(&full_bar[threadIdx.x], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const int slot = threadIdx.x / TPF;
+    const int ltid = threadIdx.x % TPF;
+    float2* buf = tw + C::TW + (size_t)slot * C::BUF;
+    constexpr uint32_t kFrameBytes = (uint32_t)(C::N * sizeof(float2));
+    static_assert(!STAGED || C::BUF >= C::N, "the exchange buffer doubles as the staging buffer");
+
+    auto slot_sync = [&]() {
+        if constexpr (TPF == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(TPF) : "memory");
+    };
+
+    // contiguous range of (channel, frame) items for this slot
+    const long long total = (long long)a.n_channels * a.n_frames;
+    const long long n_slots = (long long)gridDim.x * C::SLOTS;
+    const long long per = (total + n_slots - 1) / n_slots;
+    const long long sg = (long long)blockIdx.x * C::SLOTS + slot;
+    long long f = sg * per;
+    const long long f_end = f + per < total ? f + per : total;
+    if (f >= f_end) return;                      // (slots own whole warps and their own barrier id)
+    long long c = f / a.n_frames;
+    long long frame = f - c * a.n_frames;
+    const int nbins = a.bin_hi - a.bin_lo;
+    const float* wp = a.window + ltid;
+    uint32_t parity = 0;
+    if constexpr (STAGED) {
+        if (ltid == 0) {
+            mbar_expect_tx(&full_bar[slot], kFrameBytes);
+            bulk_load(buf, a.x + c * a.x_ch_stride + frame * a.hop, kFrameBytes, &full_bar[slot]);
+        }
+    }
+
+    for (; f < f_end; ++f) {
+        float2 v[E];
+        if constexpr (STAGED) {
+            float w[RA];
+#pragma unroll
+            for (int r = 0; r < RA; ++r) w[r] = __ldg(wp + r * RB);
+            mbar_wait(&full_bar[slot], parity);
+            parity ^= 1;
+#pragma unroll
+            for (int r = 0; r < RA; ++r) v[r] = cscale(buf[ltid + r * RB], w[r]);
+        } else {
+            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
+#pragma unroll
+            for (int r = 0; r < RA; ++r) v[r] = ldg_stream(src + r * RB);
+#pragma unroll
+            for (int r = 0; r < RA; ++r) v[r] = cscale(v[r], __ldg(wp + r * RB));
+        }
+        bfly_big<RA>(v);
+
+        slot_sync();                             // every thread of the slot has read the previous frame's M
+        {
+            float4* row = reinterpret_cast<float4*>(buf + ltid * ROW);
+#pragma unroll
+            for (int k = 0; k < RA; k += 2) row[k / 2] = make_float4(v[k].x, v[k].y, v[k + 1].x, v[k + 1].y);
+        }
+        slot_sync();
+
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int jB = ltid + q * TPF;
+            float2* u = v + q * RB;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) u[r] = buf[r * ROW + jB];
+        }
+        // (channel, frame) of the next item
+        const long long c_cur = c, frame_cur = frame;
+        if (++frame == a.n_frames) { frame = 0; ++c; }
+        if constexpr (STAGED) {
+            slot_sync();                         // M has been read by every thread: the buffer is free
+            if (ltid == 0 && f + 1 < f_end) {
+                fence_proxy_async();             // generic-proxy reads above before the async-proxy writes
+                mbar_expect_tx(&full_bar[slot], kFrameBytes);
+                bulk_load(buf, a.x + c * a.x_ch_stride + frame * a.hop, kFrameBytes, &full_bar[slot]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int jB = ltid + q * TPF;
+            float2* u = v + q * RB;
+            float2 A[C::NA8];
+#pragma unroll
+            for (int k = 1; k < C::NA8; ++k) A[k] = tw[(k - 1) * RA + jB];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                float2 B = make_float2(1.f, 0.f);
+                if (b > 0) B = tw[(C::NA8 - 1 + b - 1) * RA + jB];
+#pragma unroll
+                for (int k = 0; k < C::NA8; ++k) {
+                    if (k == 0 && b == 0) continue;
+                    const float2 t = k == 0 ? B : (b == 0 ? A[k] : cmul(A[k], B));
+                    u[8 * k + b] = cmul(u[8 * k + b], t);
+                }
+            }
+            bfly_big<RB>(u);
+        }
+
+        const long long row0 = c_cur * a.out_ch_stride + frame_cur * (long long)nbins - a.bin_lo;
+        if constexpr (MODE == IQW_STFT_DB) {
+            // branch-free dB of all the thread's bins first (64 independent MUFU chains); the rare argument
+            // that needs log10f (zero, denormal, inf, nan) is patched afterwards behind ONE branch per frame
+            bool all_ok = true;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const float arg = fabsf(v[i].x * v[i].x + v[i].y * v[i].y) + a.eps;
+                bool ok;
+                const float d = power_to_dB_fast(arg, ok);
+                all_ok &= ok;
+                v[i] = make_float2(d, arg);
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int i = 0; i < E; ++i)
+                    if (!dB_fast_ok(v[i].y)) v[i].x = power_to_dB_slow(v[i].y);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int k = ltid + q * TPF + r * RA;
+                if (FULLBAND || (k >= a.bin_lo && k < a.bin_hi)) {
+                    const float2 X = v[q * RB + r];
+                    if constexpr (MODE == IQW_STFT_COMPLEX) {
+                        __stcs(reinterpret_cast<float2*>(a.out) + row0 + k, X);
+                    } else if constexpr (MODE == IQW_STFT_DB) {
+                        __stcs(reinterpret_cast<float*>(a.out) + row0 + k, X.x);
+                    } else {
+                        __stcs(reinterpret_cast<float*>(a.out) + row0 + k, X.x * X.x + X.y * X.y);
+                    }
+                }
+            }
+    }
+}
+
+// W_N^(r*jB) tables of the two-pass kernels, one immutable table per (device, log2 nfft)
+__global__ void twiddle2p_init_kernel(float2* tw, int n, int ra, int rb) {
+    const int na8 = rb / 8;
+    const int count = (na8 - 1 + 7) * ra;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const int row = e / ra, j = e % ra;
+        const int r = row < na8 - 1 ? 8 * (row + 1) : row - (na8 - 1) + 1;      // A rows: r = 8a, B rows: r = b
+        double s, c;
+        sincospi(-2.0 * (double)(r * j) / (double)n, &s, &c);
+        tw[e] = make_float2((float)c, (float)s);
+    }
+}
+
+static std::mutex g_tw2_mutex;
+static std::map<std::pair<int, int>, float2*> g_tw2_cache;
+
+template <int LOG2N>
+static int get_twiddles2p(cudaStream_t stream, const float2** out) {
+    using C = P2Cfg<LOG2N, true>;
+    int dev = 0;
+    IQW_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tw2_mutex);
+    auto key = std::make_pair(dev, LOG2N);
+    auto it = g_tw2_cache.find(key);
+    if (it == g_tw2_cache.end()) {
+        float2* d = nullptr;
+        IQW_CUDA_OK(cudaMalloc(&d, sizeof(float2) * C::TW));
+        twiddle2p_init_kernel<<<16, 256, 0, stream>>>(d, C::N, C::RA, C::RB);
+        IQW_CUDA_OK(cudaGetLastError());
+        IQW_CUDA_OK(cudaStreamSynchronize(stream));   // one-time: visible to every later stream
+        it = g_tw2_cache.emplace(key, d).first;
+    }
+    *out = it->second;
+    return IQW_OK;
+}
+
+template <int LOG2N, int MODE, bool FULLBAND, bool STAGED>
+static int launch2p_staged(StftArgs a, cudaStream_t stream) {
+    using C = P2Cfg<LOG2N, STAGED>;
+    auto kern = stft2p_kernel<LOG2N, MODE, FULLBAND, STAGED>;
+    if (int rc = get_twiddles2p<LOG2N>(stream, &a.twiddle)) return rc;
+    IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    int sms = 0, per_sm = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    IQW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM));
+    if (per_sm < 1) return fail(IQW_ERR_CUDA, "two-pass stft kernel nfft=%d does not fit on an SM", C::N);
+    const long long total = (long long)a.n_channels * a.n_frames;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (total + C::SLOTS - 1) / C::SLOTS;
+    if (grid > need) grid = need;
+    { IQW_PROFILE("stft_kernel", stream); kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(a); }
+    IQW_CUDA_OK(cudaGetLastError());
+    return IQW_OK;
+}
+
+static std::atomic<int> g_stft_variant{0};   // 0 = auto, 1 = three-pass, 2 = two-pass with global loads, 3 = two-pass staged
+
+// a bulk copy needs 16-byte aligned source addresses: every frame start of every channel
+static bool frames_16B_aligned(const StftArgs& a) {
+    return (reinterpret_cast<uintptr_t>(a.x) % 16 == 0) && (a.hop % 2 == 0) && (a.n_channels == 1 || a.x_ch_stride % 2 == 0);
+}
+
+template <int LOG2N, int MODE, bool FULLBAND>
+static int launch2p_band(const StftArgs& a, cudaStream_t stream) {
+    if (g_stft_variant.load() != 2 && frames_16B_aligned(a)) return launch2p_staged<LOG2N, MODE, FULLBAND, true>(a, stream);
+    return launch2p_staged<LOG2N, MODE, FULLBAND, false>(a, stream);
+}
+
+template <int LOG2N>
+static int launch2p(const StftArgs& a, int mode, cudaStream_t s) {
+    const bool full = a.bin_lo == 0 && a.bin_hi == (1 << LOG2N);
+    switch (mode) {
+        case IQW_STFT_COMPLEX:
+            return full ? launch2p_band<LOG2N, IQW_STFT_COMPLEX, true>(a, s) : launch2p_band<LOG2N, IQW_STFT_COMPLEX, false>(a, s);
+        case IQW_STFT_POWER:
+            return full ? launch2p_band<LOG2N, IQW_STFT_POWER, true>(a, s) : launch2p_band<LOG2N, IQW_STFT_POWER, false>(a, s);
+        case IQW_STFT_DB:
+            return full ? launch2p_band<LOG2N, IQW_STFT_DB, true>(a, s) : launch2p_band<LOG2N, IQW_STFT_DB, false>(a, s);
+    }
+    return fail(IQW_ERR_INVALID, "unknown stft mode %d", mode);
+}
+
+bool stft_two_pass_wanted(int log2n) {
+    if (log2n < 10 || log2n > 12) return false;
+    return g_stft_variant.load() != 1;
+}
+
+int launch_stft_two_pass(const StftArgs& a, int log2n, int mode, cudaStream_t stream) {
+    switch (log2n) {
+        case 10: return launch2p<10>(a, mode, stream);
+        case 11: return launch2p<11>(a, mode, stream);
+        case 12: return launch2p<12>(a, mode, stream);
+    }
+    return fail(IQW_ERR_UNSUPPORTED, "two-pass stft: nfft=%d", 1 << log2n);
+}
+
+}  // namespace iqw
+
+extern "C" int iqw_debug_set_stft_variant(int variant) {
+    if (variant < 0 || variant > 3)
+        return iqw::fail(IQW_ERR_INVALID, "variant must be 0 (auto), 1 (three-pass), 2 (two-pass, global loads) or 3 (two-pass, staged)");
+    iqw::g_stft_variant.store(variant);
+    return IQW_OK;
+}

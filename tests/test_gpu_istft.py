@@ -101,18 +101,29 @@ def test_ola_filter_matches_oracle(passband, shape, axis):
 
 @pytest.mark.parametrize('nfft', [16, 64, 256, 1024, 2048, 4096, 8192])
 def test_fused_ola_filter_equals_the_two_kernel_chain(nfft):
-    """one kernel (no STFT in memory) against stft -> masked istft: the same arithmetic, bit for bit"""
+    """one kernel (no STFT in memory) against stft -> masked istft.  With the forward transform of the
+    chain on the three-pass geometry the fused kernel shares (variant 1) it is the same arithmetic, bit
+    for bit; with the default forward kernel (two-pass at nfft 1024..4096) the two differ by float32
+    rounding only (waveform tolerance of tests/_tol.py)."""
+    from iqwaveform_b200 import _lib
     x = torch.from_numpy(synth(nfft, (3, nfft * 40))).cuda()
     e = float(orc.enbw_symmetric('hamming', nfft))
-    for pb in [(-2e5, 2e5), (-e - 2e-6 * 512 / nfft, e + 1e-6 * 512 / nfft)]:
-        kw = dict(fs=1e6, nfft=nfft, window='hamming', passband=pb, axis=1)
-        a = iqw.ola_filter(x, **kw)
-        b = iqw.ola_filter(x, fused=False, **kw)
-        assert torch.equal(a, b)
-    # a long capture: many frame ranges per channel
-    x = torch.from_numpy(synth(1, (2, nfft * 3000 if nfft <= 256 else nfft * 300))).cuda()
-    kw = dict(fs=1e6, nfft=nfft, window='hamming', passband=(-1e5, 1e5), axis=1)
-    assert torch.equal(iqw.ola_filter(x, **kw), iqw.ola_filter(x, fused=False, **kw))
+    try:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(1))
+        for pb in [(-2e5, 2e5), (-e - 2e-6 * 512 / nfft, e + 1e-6 * 512 / nfft)]:
+            kw = dict(fs=1e6, nfft=nfft, window='hamming', passband=pb, axis=1)
+            a = iqw.ola_filter(x, **kw)
+            b = iqw.ola_filter(x, fused=False, **kw)
+            assert torch.equal(a, b)
+        # a long capture: many frame ranges per channel
+        xl = torch.from_numpy(synth(1, (2, nfft * 3000 if nfft <= 256 else nfft * 300))).cuda()
+        kw = dict(fs=1e6, nfft=nfft, window='hamming', passband=(-1e5, 1e5), axis=1)
+        fused = iqw.ola_filter(xl, **kw)
+        assert torch.equal(fused, iqw.ola_filter(xl, fused=False, **kw))
+    finally:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(0))
+    chain = iqw.ola_filter(xl, fused=False, **kw).cpu().numpy()
+    assert np.all(np.abs(chain - fused.cpu().numpy()) <= _tol.waveform_tol(fused.cpu().numpy()))
 
 
 def test_errors_follow_the_reference():

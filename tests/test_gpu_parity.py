@@ -426,3 +426,40 @@ def test_persistence_streams_host_captures(cuda_device, monkeypatch):
     pinned = torch.from_numpy(x[0]).pin_memory()
     got = iqw.persistence_spectrum(pinned, **dict(kw, axis=0))        # 1-D pinned torch in -> CPU torch out
     assert isinstance(got, torch.Tensor) and not got.is_cuda and np.array_equal(got.numpy(), want[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel-1 geometries at nfft 1024 / 2048 / 4096: three-pass, two-pass with global loads, two-pass
+# with bulk-copy (TMA) staging -- same transform, every variant against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('variant', [1, 2, 3])
+@pytest.mark.parametrize('nfft,nov', [(1024, 512), (2048, 1536), (4096, 2048), (4096, 0), (1024, 511), (2048, 1)])
+def test_stft_kernel_variants_vs_oracle(cuda_device, variant, nfft, nov):
+    """(1024, 511) and (2048, 1) have an odd hop: frame starts are not 16-byte aligned, so the staged
+    kernel must hand over to the global-load one (variant 3 is a request, not a guarantee)"""
+    from iqwaveform_b200 import _lib
+    x = synth(nfft + nov, (3, nfft * 9 + 13))
+    _, _, ref = orc.stft(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm='power')
+    _, _, pref = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1)
+    try:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(variant))
+        y = iqw.stft(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1,
+                     norm='power', return_axis_arrays=False).cpu().numpy()
+        p = iqw.spectrogram(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1,
+                            return_axis_arrays=False).cpu().numpy()
+        # odd channel stride (a view of a wider buffer) and a band trim
+        wide = torch.zeros((3, x.shape[1] + 1), dtype=torch.complex64, device=cuda_device)
+        wide[:, :-1] = dev_of(x, cuda_device)
+        pb = iqw.persistence_spectrum(wide[:, :-1], fs=1e6, window='hann', resolution=1e6 / nfft,
+                                      fractional_overlap=nov / nfft, statistics=['max'], dB=False, axis=1,
+                                      bandwidth=0.5e6) if nov * 2 == nfft else None
+    finally:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(0))
+    assert (np.abs(y - ref) / _tol.complex_tol(ref)).max() <= 1.0
+    assert _tol.power_err_units(p, pref) <= 1.0
+    if pb is not None:
+        lo, hi = nfft // 4, nfft - nfft // 4
+        want = pref.max(axis=1)[:, lo:hi]
+        got = pb.cpu().numpy()[:, 0]
+        assert got.shape == want.shape
+        assert np.all(np.abs(got - want) <= _tol.POWER_RTOL * want + _tol.POWER_FLOOR * pref.max())
