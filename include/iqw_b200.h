@@ -93,6 +93,24 @@ int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t
                  float eps, int32_t bin_lo, int32_t bin_hi, void* d_out,
                  int64_t out_channel_stride, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Kernel 1 with the reducible time statistics fused into its epilogue: persistence spectrum with
+ * statistics drawn from {mean, rms, max, peak, min} WITHOUT materialising the spectrogram (8 B per
+ * sample of HBM traffic instead of 24).  Replaces fourier.py:1287-1301 (spectrogram, band slice, powtodB)
+ * + fourier.py:1322-1325 (np.max / np.min / np.mean over the time axis) for that case.  Every frame slot
+ * of the grid keeps max, min and a compensated sum of the bins it owns over its frames; a small second
+ * kernel combines the partial rows.  mean averages the dB values when to_dB (like the reference, which
+ * converts the spectrogram first); max / min are taken on the power and converted once (monotone map).
+ *   stats        kinds IQW_STAT_MEAN / MAX / MIN only (others: IQW_ERR_UNSUPPORTED)
+ *   nfft         power of two, 16 <= nfft <= 8192
+ *   d_out        (n_channels, n_stats, bin_hi - bin_lo) float32
+ *   d_workspace  >= iqw_stft_reduce_workspace_bytes(nfft) bytes
+ * The other arguments are those of iqw_stft_c64. */
+size_t iqw_stft_reduce_workspace_bytes(int32_t nfft);
+int iqw_stft_reduce_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,
+                        const float* d_window, int32_t nfft, int64_t hop, int64_t n_frames, int32_t to_dB,
+                        float eps, int32_t bin_lo, int32_t bin_hi, const iqw_stat* stats, int32_t n_stats,
+                        float* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Kernel 2: statistics over the time axis of a (n_channels, n_rows, n_cols) float32 matrix
  * (rows = frames, cols = bins): exact order statistics + numpy 'linear' lerp, mean, max, min.

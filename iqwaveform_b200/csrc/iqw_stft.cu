@@ -22,8 +22,10 @@
 namespace iqw {
 
 // FULLBAND: every bin is stored (bin_lo == 0, bin_hi == nfft), so the per-bin range checks vanish
+// MODE == kStftReduce: the 48-64 accumulator registers per thread leave room for one CTA per SM only
+// (measured on the plain kernel: one CTA per SM costs 6 %), but no spectrogram is written at all
 template <int LOG2N, int MODE, bool FULLBAND>
-__global__ void __launch_bounds__(StftCfg<LOG2N>::THREADS, StftCfg<LOG2N>::MIN_BLOCKS)
+__global__ void __launch_bounds__(StftCfg<LOG2N>::THREADS, MODE == kStftReduce ? 1 : StftCfg<LOG2N>::MIN_BLOCKS)
 stft_kernel(const StftArgs a) {
     using C = StftCfg<LOG2N>;
     constexpr int N = C::N, E = C::E, TPF = C::TPF, FPC = C::FPC;
@@ -54,6 +56,15 @@ stft_kernel(const StftArgs a) {
     const long long g_end = g_begin + per < a.n_groups ? g_begin + per : a.n_groups;
     const int nbins = a.bin_hi - a.bin_lo;
     int par = 0;
+
+    // running statistics of the bins this thread owns (kStftReduce): max, min and a two-level sum (the
+    // inner sum runs over 32 frames, the outer over the inner sums, so that thousands of frames add up
+    // with the rounding error of a few dozen additions)
+    constexpr int EA = MODE == kStftReduce ? E : 1;
+    float acc_mx[EA], acc_mn[EA], acc_s[EA], acc_big[EA];
+#pragma unroll
+    for (int e = 0; e < EA; ++e) { acc_mx[e] = -INFINITY; acc_mn[e] = INFINITY; acc_s[e] = 0.f; acc_big[e] = 0.f; }
+    int acc_n = 0;
 
     // (channel, frame group) of g_begin, then advanced incrementally: no 64-bit divisions in the loop
     long long c_nx = g_begin / a.groups_per_ch;
@@ -89,7 +100,46 @@ stft_kernel(const StftArgs a) {
 
         PassLoop<LOG2N, 0>::run(v, bufs, tw, nullptr, ltid, slot, par);
 
-        if (valid) {
+        if constexpr (MODE == kStftReduce) {
+            if (valid) {
+                float p[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) p[e] = v[e].x * v[e].x + v[e].y * v[e].y;
+                if (a.reduce_flags & 1) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) { acc_mx[e] = fmaxf(acc_mx[e], p[e]); acc_mn[e] = fminf(acc_mn[e], p[e]); }
+                }
+                if (a.reduce_flags & 2) {
+                    if (a.reduce_dB) {
+                        // branch-free dB of the 16 values (independent MUFU chains); an argument that needs
+                        // log10f (zero, denormal, inf, nan) is rare and patched behind one branch per frame
+                        bool all_ok = true;
+                        float d[E];
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            bool ok;
+                            d[e] = power_to_dB_fast(fabsf(p[e]) + a.eps, ok);
+                            all_ok &= ok;
+                        }
+                        if (!all_ok) {
+#pragma unroll
+                            for (int e = 0; e < E; ++e)
+                                if (!dB_fast_ok(fabsf(p[e]) + a.eps)) d[e] = power_to_dB_slow(fabsf(p[e]) + a.eps);
+                        }
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc_s[e] += d[e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc_s[e] += p[e];
+                    }
+                    if (++acc_n == 32) {
+                        acc_n = 0;
+#pragma unroll
+                        for (int e = 0; e < E; ++e) { acc_big[e] += acc_s[e]; acc_s[e] = 0.f; }
+                    }
+                }
+            }
+        } else if (valid) {
             const long long row = c * a.out_ch_stride + frame * (long long)nbins - a.bin_lo;
 #pragma unroll
             for (int q = 0; q < E / RL; ++q)
@@ -111,6 +161,47 @@ stft_kernel(const StftArgs a) {
         // no trailing barrier needed: the ping-pong parity keeps an exchange buffer from being
         // rewritten before every thread has passed the barrier that follows its last read
         if constexpr (C::NP == 1) { /* no shared memory exchange at all */ }
+    }
+    if constexpr (MODE == kStftReduce) {
+        // one partial row per frame slot of the grid (slots that saw no frame write the neutral elements)
+        const long long part = ((long long)blockIdx.x * FPC + slot) * N;
+#pragma unroll
+        for (int q = 0; q < E / RL; ++q)
+#pragma unroll
+            for (int r = 0; r < RL; ++r) {
+                const int k = (ltid + q * TPF) + r * (N / RL);
+                const int e = q * RL + r;
+                a.part_max[part + k] = acc_mx[e];
+                a.part_min[part + k] = acc_mn[e];
+                a.part_sum[part + k] = (double)acc_big[e] + (double)acc_s[e];
+            }
+    }
+}
+
+// max / min / sum over the partial rows of one channel, then the named statistics of the request
+// (fourier.py:1322-1325: np.max / np.min / np.mean over the time axis of the (dB) spectrogram).  dB is
+// monotone, so max and min are taken on the power and converted once.
+struct ReducePlan { int n_stats; int kind[16]; };
+__global__ void stft_reduce_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ pmin,
+                                           const double* __restrict__ psum, int n_parts, int nfft, int bin_lo,
+                                           int bin_hi, long long n_frames, ReducePlan st, int to_dB, float eps,
+                                           float* __restrict__ out /* [n_stats][bin_hi - bin_lo] */) {
+    const int k = bin_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bin_hi) return;
+    float mx = -INFINITY, mn = INFINITY;
+    double sum = 0.0;
+    for (int p = 0; p < n_parts; ++p) {
+        mx = fmaxf(mx, pmax[(long long)p * nfft + k]);
+        mn = fminf(mn, pmin[(long long)p * nfft + k]);
+        sum += psum[(long long)p * nfft + k];
+    }
+    const int nb = bin_hi - bin_lo;
+    for (int t = 0; t < st.n_stats; ++t) {
+        float r;
+        if (st.kind[t] == IQW_STAT_MEAN) r = (float)(sum / (double)n_frames);
+        else if (st.kind[t] == IQW_STAT_MAX) r = to_dB ? power_to_dB(mx, eps) : mx;
+        else r = to_dB ? power_to_dB(mn, eps) : mn;
+        out[(long long)t * nb + (k - bin_lo)] = r;
     }
 }
 
@@ -187,9 +278,104 @@ static int launch_stft_mode(const StftArgs& a, int mode, cudaStream_t s) {
     return fail(IQW_ERR_INVALID, "unknown stft mode %d", mode);
 }
 
+template <int LOG2N>
+static int launch_stft_reduce(StftArgs a, const ReducePlan& st, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    using C = StftCfg<LOG2N>;
+    auto kern = stft_kernel<LOG2N, kStftReduce, true>;
+    IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    int sms = 0, per_sm = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    IQW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM));
+    if (per_sm < 1) return fail(IQW_ERR_CUDA, "stft reduce kernel nfft=%d does not fit on an SM", C::N);
+    a.n_channels = 1;
+    a.groups_per_ch = (a.n_frames + C::FPC - 1) / C::FPC;
+    a.n_groups = a.groups_per_ch;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.n_groups) grid = a.n_groups;
+    const long long n_parts = grid * C::FPC;
+    const size_t need = (size_t)n_parts * C::N * (2 * sizeof(float) + sizeof(double));
+    if (!ws || ws_bytes < need) return fail(IQW_ERR_WORKSPACE, "stft reduce workspace %zu bytes < required %zu", ws_bytes, need);
+    a.part_sum = static_cast<double*>(ws);
+    a.part_max = reinterpret_cast<float*>(a.part_sum + n_parts * C::N);
+    a.part_min = a.part_max + n_parts * C::N;
+    { IQW_PROFILE("stft_reduce_kernel", stream); kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(a); }
+    IQW_CUDA_OK(cudaGetLastError());
+    const int nb = a.bin_hi - a.bin_lo;
+    { IQW_PROFILE_FINE("stft_reduce_combine", stream);
+      stft_reduce_combine_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(a.part_max, a.part_min, a.part_sum, (int)n_parts, C::N,
+                                                                       a.bin_lo, a.bin_hi, a.n_frames, st, a.reduce_dB, a.eps, out); }
+    IQW_CUDA_OK(cudaGetLastError());
+    return IQW_OK;
+}
+
 }  // namespace iqw
 
 using namespace iqw;
+
+// partial rows: at most (SMs * 2 CTAs) * 16 frame slots, 16 bytes per bin each
+extern "C" size_t iqw_stft_reduce_workspace_bytes(int32_t nfft) {
+    if (nfft < 16 || nfft > 8192 || (nfft & (nfft - 1))) return 0;
+    int sms = 0;
+    if (device_sm_count(&sms) != IQW_OK) sms = 160;
+    return (size_t)sms * 2 * 16 * (size_t)nfft * 16;
+}
+
+extern "C" int iqw_stft_reduce_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,
+                                   const float* d_window, int32_t nfft, int64_t hop, int64_t n_frames, int32_t to_dB,
+                                   float eps, int32_t bin_lo, int32_t bin_hi, const iqw_stat* stats, int32_t n_stats,
+                                   float* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_x);
+    if (!d_x || !d_window || !d_out || !stats) return fail(IQW_ERR_INVALID, "null pointer argument");
+    if (nfft < 16 || nfft > 8192 || (nfft & (nfft - 1)))
+        return fail(IQW_ERR_UNSUPPORTED, "iqw_stft_reduce_c64: nfft=%d: powers of two from 16 to 8192 are built", nfft);
+    if (hop < 1 || n_channels < 1 || n_frames < 1) return fail(IQW_ERR_INVALID, "need hop, n_channels, n_frames >= 1");
+    if ((n_frames - 1) * hop + nfft > n_samples)
+        return fail(IQW_ERR_INVALID, "n_frames=%lld does not fit in n_samples=%lld", (long long)n_frames, (long long)n_samples);
+    if (bin_lo < 0 || bin_hi > nfft || bin_lo >= bin_hi) return fail(IQW_ERR_INVALID, "bad bin range [%d, %d)", bin_lo, bin_hi);
+    if (n_stats < 1 || n_stats > 16) return fail(IQW_ERR_INVALID, "1 <= n_stats <= 16");
+    ReducePlan st{};
+    st.n_stats = n_stats;
+    for (int t = 0; t < n_stats; ++t) {
+        if (stats[t].kind != IQW_STAT_MEAN && stats[t].kind != IQW_STAT_MAX && stats[t].kind != IQW_STAT_MIN)
+            return fail(IQW_ERR_UNSUPPORTED, "iqw_stft_reduce_c64 takes mean / max / min only (order statistics need the spectrogram)");
+        st.kind[t] = stats[t].kind;
+    }
+    int log2n = 0;
+    while ((1 << log2n) < nfft) ++log2n;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int nb = bin_hi - bin_lo;
+    for (int64_t c = 0; c < n_channels; ++c) {
+        StftArgs a{};
+        a.x = static_cast<const float2*>(d_x) + c * x_channel_stride;
+        a.n_samples = n_samples;
+        a.x_ch_stride = x_channel_stride;
+        a.window = d_window;
+        a.hop = hop;
+        a.n_frames = n_frames;
+        a.eps = eps;
+        a.bin_lo = bin_lo;
+        a.bin_hi = bin_hi;
+        a.reduce_dB = to_dB ? 1 : 0;
+        for (int t = 0; t < n_stats; ++t) a.reduce_flags |= stats[t].kind == IQW_STAT_MEAN ? 2 : 1;
+        if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;
+        float* out = d_out + c * (int64_t)n_stats * nb;
+        int rc = IQW_ERR_UNSUPPORTED;
+        switch (log2n) {
+            case 4: rc = launch_stft_reduce<4>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 5: rc = launch_stft_reduce<5>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 6: rc = launch_stft_reduce<6>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 7: rc = launch_stft_reduce<7>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 8: rc = launch_stft_reduce<8>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 9: rc = launch_stft_reduce<9>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 10: rc = launch_stft_reduce<10>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 11: rc = launch_stft_reduce<11>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 12: rc = launch_stft_reduce<12>(a, st, out, d_workspace, workspace_bytes, s); break;
+            case 13: rc = launch_stft_reduce<13>(a, st, out, d_workspace, workspace_bytes, s); break;
+        }
+        if (rc) return rc;
+    }
+    return IQW_OK;
+}
 
 extern "C" size_t iqw_stft_workspace_bytes(int32_t nfft, int64_t n_channels, int64_t n_frames) {
     if (nfft < 2 || (nfft & (nfft - 1))) return 0;

@@ -19,7 +19,16 @@ struct StftArgs {
     long long out_ch_stride;
     long long n_groups;        // n_channels * groups_per_channel
     long long groups_per_ch;   // ceil(n_frames / FPC)
+    // MODE == kStftReduce (iqw_stft_reduce_c64): nothing is stored per frame; every frame slot keeps the
+    // running max / min / sum over its frames of each bin it owns and writes one partial row at the end
+    float* part_max;           // [n_parts][nfft]
+    float* part_min;
+    double* part_sum;          // sum of the power, or of its dB when reduce_dB
+    int reduce_dB;
+    int reduce_flags;          // bit 0: max / min wanted, bit 1: sum wanted
 };
+
+constexpr int kStftReduce = 3;   // internal mode of stft_kernel, next to IQW_STFT_COMPLEX / POWER / DB
 
 // geometry of the in-CTA FFT (shared by the forward kernel, iqw_stft.cu, and the inverse one,
 // iqw_istft.cu)

@@ -621,6 +621,12 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
     xd, res = _arrays.to_device(x)
     x2, lead, trail = _arrays.as_channels(xd, axis)
 
+    if _reducible(statistics, nfft) and x2.dtype == torch.complex64:
+        # mean / max / min only: fused into kernel 1, no spectrogram in memory (8 B/sample of HBM traffic)
+        out = _psd_reduce_device(x2, window=window, nfft=nfft, noverlap=noverlap, nzero=nzero, bin_lo=bin_lo,
+                                 bin_hi=bin_hi, statistics=statistics, dB=dB)
+        return res.give_back(_arrays.restore_layout(out, lead, trail, 2))
+
     C = x2.shape[0]
     dev = x2.device
     out = torch.empty((C, len(statistics), bin_hi - bin_lo), dtype=torch.float32, device=dev)
@@ -656,6 +662,59 @@ def power_spectral_density(x, *, fs: float, bandwidth=INF, window, resolution: f
         for c in range(C):      # one channel's spectrogram in flight at a time (8 GB at config 3)
             scratch = one_channel(c, scratch)
     return res.give_back(_arrays.restore_layout(out, lead, trail, 2))
+
+
+def _reducible(statistics, nfft: int) -> bool:
+    """statistics that combine over time without the spectrogram (fourier.py:1322-1325 for 'max', 'min',
+    'mean' and their aliases), at a frame size the fused kernel is built for"""
+    if nfft < 16 or nfft > 8192 or nfft & (nfft - 1):
+        return False
+    kinds = {r.kind for r in _plan.stat_requests(list(statistics), 2)}
+    return bool(kinds) and kinds <= {_lib.STAT_MEAN, _lib.STAT_MAX, _lib.STAT_MIN}
+
+
+def _psd_reduce_device(x2: torch.Tensor, *, window, nfft, noverlap, nzero, bin_lo, bin_hi, statistics, dB,
+                       frames: tuple | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(C, N) complex64 on the device -> (C, nstat, nbins) through iqw_stft_reduce_c64.  `frames=(f0, f1)`
+    reduces only that frame range (C must be 1): the host path combines such partial results."""
+    C, N = x2.shape
+    hop = nfft - noverlap
+    T = _frame_count(N, nfft, noverlap, True)
+    if T < 1:
+        raise ValueError('cannot take statistics over zero frames')
+    f0, f1 = (0, T) if frames is None else frames
+    reqs = _plan.stat_requests(list(statistics), f1 - f0)
+    nb = bin_hi - bin_lo
+    w = _device_window(window, nfft, nzero, 'power', hop, x2.device)
+    if out is None:
+        out = torch.empty((C, len(reqs), nb), dtype=torch.float32, device=x2.device)
+    ws_bytes = _lib.lib.iqw_stft_reduce_workspace_bytes(nfft)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device)
+    arr = (_lib.iqw_stat * len(reqs))(*reqs)
+    _lib.check(_lib.lib.iqw_stft_reduce_c64(
+        ctypes.c_void_p(x2.data_ptr() + f0 * hop * 8), C, (f1 - f0 - 1) * hop + nfft if frames is not None else N,
+        x2.stride(0) if C > 1 else N, ctypes.c_void_p(w.data_ptr()), nfft, hop, f1 - f0, int(bool(dB)), 1e-25,
+        bin_lo, bin_hi, arr, len(reqs), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws_bytes,
+        _stream_ptr(x2.device)))
+    return out
+
+
+def _combine_reduced(parts: list, counts: list, statistics) -> torch.Tensor:
+    """combine (nstat, nbins) results of consecutive frame ranges: max of max, min of min, frame-count
+    weighted mean of means (in float64)"""
+    kinds = [r.kind for r in _plan.stat_requests(list(statistics), 2)]
+    stack = torch.stack(parts)                      # (n_parts, nstat, nbins)
+    wts = torch.tensor(counts, dtype=torch.float64, device=stack.device)
+    rows = []
+    for i, k in enumerate(kinds):
+        col = stack[:, i]
+        if k == _lib.STAT_MAX:
+            rows.append(col.amax(0))
+        elif k == _lib.STAT_MIN:
+            rows.append(col.amin(0))
+        else:
+            rows.append(((col.double() * wts[:, None]).sum(0) / wts.sum()).float())
+    return torch.stack(rows)
 
 
 PIPELINE_MIN_BYTES = 64 << 20    # spectrograms at least this large: two-stream pipeline over channels
@@ -697,19 +756,21 @@ def _psd_from_host(xh, kind, squeeze, *, window, nfft, noverlap, nzero, bin_lo, 
     T = _frame_count(N, nfft, noverlap, True)
     nb = bin_hi - bin_lo
     out = torch.empty((C, len(statistics), nb), dtype=torch.float32, device=dev)
-    spg = torch.empty((1, T, nb), dtype=torch.float32, device=dev)
+    spg = None if _reducible(statistics, nfft) else torch.empty((1, T, nb), dtype=torch.float32, device=dev)
     bufs = [torch.empty((1, N), dtype=torch.complex64, device=dev) for _ in range(min(C, 2))]
     for b in bufs:
         b.record_stream(cs)
     step = -(-N // STREAM_CHUNKS)
     step = max(nfft, -(-step // hop) * hop)
     freed = [None, None]                      # event after the last kernel that read bufs[i]
+    fused = _reducible(statistics, nfft)      # mean / max / min only: each chunk is reduced as it lands
     for c in range(C):
         xd = bufs[c % 2]
         cs.wait_stream(main) if c == 0 else None
         if freed[c % 2] is not None:
             cs.wait_event(freed[c % 2])
         done = 0
+        parts, counts = [], []
         for s0 in range(0, N, step):
             s1 = min(N, s0 + step)
             with torch.cuda.stream(cs):
@@ -718,12 +779,21 @@ def _psd_from_host(xh, kind, squeeze, *, window, nfft, noverlap, nzero, bin_lo, 
             main.wait_event(ev)
             f1 = min(T, (s1 - nfft) // hop + 1) if s1 >= nfft else 0
             if f1 > done:
-                _stft_device(xd, window=window, nfft=nfft, noverlap=noverlap, nzero=nzero, norm='power',
-                             truncate=True, mode=_lib.STFT_POWER, bin_lo=bin_lo, bin_hi=bin_hi, out=spg,
-                             frames=(done, f1))
+                if fused:
+                    parts.append(_psd_reduce_device(xd, window=window, nfft=nfft, noverlap=noverlap, nzero=nzero,
+                                                    bin_lo=bin_lo, bin_hi=bin_hi, statistics=statistics, dB=dB,
+                                                    frames=(done, f1))[0])
+                    counts.append(f1 - done)
+                else:
+                    _stft_device(xd, window=window, nfft=nfft, noverlap=noverlap, nzero=nzero, norm='power',
+                                 truncate=True, mode=_lib.STFT_POWER, bin_lo=bin_lo, bin_hi=bin_hi, out=spg,
+                                 frames=(done, f1))
                 done = f1
         freed[c % 2] = main.record_event()
-        time_statistics(spg, statistics, dB=bool(dB), eps=1e-25, out=out[c:c + 1])
+        if fused:
+            out[c] = _combine_reduced(parts, counts, statistics)
+        else:
+            time_statistics(spg, statistics, dB=bool(dB), eps=1e-25, out=out[c:c + 1])
     res = _arrays.Residence(kind)
     return res.give_back(out[0] if squeeze else out)
 

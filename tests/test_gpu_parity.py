@@ -463,3 +463,60 @@ def test_stft_kernel_variants_vs_oracle(cuda_device, variant, nfft, nov):
         got = pb.cpu().numpy()[:, 0]
         assert got.shape == want.shape
         assert np.all(np.abs(got - want) <= _tol.POWER_RTOL * want + _tol.POWER_FLOOR * pref.max())
+
+
+# ---------------------------------------------------------------------------------------------
+# reducible statistics fused into kernel 1 (no spectrogram in memory): fourier.py:1322-1325
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,nfft,ovl,stats,kw', [
+    (1 << 18, 1024, 0.5, ['mean', 'max'], {}),
+    (1 << 19, 4096, 0.5, ['max', 'min', 'mean', 'rms', 'peak'], dict(bandwidth=0.5e6)),
+    (1 << 16, 256, 0.75, ['mean', 'max', 'min'], dict(dB=False)),
+    (1 << 17, 64, 0.0, ['min'], {}),
+    (1 << 18, 8192, 0.5, ['mean', 'peak'], {}),
+    (1 << 17, 512, 0.5, ['max'], dict(fractional_window=0.75)),
+])
+def test_fused_reducible_statistics_vs_oracle(cuda_device, n, nfft, ovl, stats, kw):
+    from iqwaveform_b200 import fourier as F
+    assert F._reducible(stats, nfft)
+    x = synth(n % 83, (2, n))
+    args = dict(fs=1e6, window='hann', resolution=1e6 / nfft, fractional_overlap=ovl,
+                statistics=stats, axis=1, **kw)
+    ref = orc.persistence_spectrum(x, **args)
+    from iqwaveform_b200 import _lib
+    _lib.profile(True)
+    got = iqw.persistence_spectrum(dev_of(x, cuda_device), **args)
+    torch.cuda.synchronize()
+    names = set(_lib.profile_report())
+    _lib.profile(False)
+    assert 'stft_reduce_kernel' in names and 'stft_kernel' not in names      # nothing was materialised
+    assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
+    nz = round((1 - kw.get('fractional_window', 1)) * nfft)
+    _, _, p = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=round(ovl * nfft), nzero=nz, axis=1)
+    _check_persistence(got.cpu().numpy(), ref, stats, x, nfft, kw.get('dB', True), p.max(axis=(1, 2))[:, None])
+    # same rows as the materialising path (statistics kernel 2) up to the mean's summation order, when the
+    # spectrogram comes from the same FFT geometry (the fused epilogue lives in the three-pass kernel)
+    try:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(1))
+        mixed = iqw.persistence_spectrum(dev_of(x, cuda_device), **dict(args, statistics=stats + [0.5]))[:, :len(stats)]
+    finally:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(0))
+    for i, s in enumerate(stats):
+        if s in ('mean', 'rms'):
+            assert torch.allclose(got[:, i], mixed[:, i], rtol=1e-5, atol=1e-4)
+        else:
+            assert torch.equal(got[:, i], mixed[:, i]), s
+
+
+def test_fused_reducible_statistics_host_capture_and_1d(cuda_device):
+    """a host capture large enough for the chunked copy path: every chunk is reduced as it lands and the
+    partial rows are combined; equals the device-resident call"""
+    n, nfft = 1 << 24, 2048         # 128 MB >= STREAM_MIN_BYTES
+    x = synth(12, (n,))
+    args = dict(fs=1e6, window='blackmanharris', resolution=1e6 / nfft, fractional_overlap=0.5,
+                statistics=['max', 'mean', 'min'], dB=True, axis=0)
+    host = iqw.persistence_spectrum(x, **args)
+    assert isinstance(host, np.ndarray) and host.shape == (3, nfft)
+    devr = iqw.persistence_spectrum(dev_of(x, cuda_device), **args).cpu().numpy()
+    assert np.array_equal(host[0], devr[0]) and np.array_equal(host[2], devr[2])
+    np.testing.assert_allclose(host[1], devr[1], atol=2e-4)
