@@ -93,6 +93,30 @@ int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t
                  float eps, int32_t bin_lo, int32_t bin_hi, void* d_out,
                  int64_t out_channel_stride, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Kernel 1 for frame lengths that are not a power of two (the reference takes nfft = round(fs/resolution),
+ * fourier.py:1250-1255, and any length goes to scipy.fft / cuFFT, fourier.py:200-218): Bluestein's chirp-z
+ * transform -- gather x window x chirp -> M-point FFT -> x filter spectrum -> M-point inverse FFT -> chirp ->
+ * epilogue -- inside one CTA, M = the power of two >= 2*nfft - 1.  The host supplies the three tables
+ * (python: iqwaveform_b200._plan.bluestein_tables, float64 design):
+ *   d_pre   nfft complex64: frame coefficient (window, (-1)^n, 1/nfft ...) times exp(-i pi n^2 / nfft)
+ *   d_bh    m complex64:    FFT_m of the wrapped chirp exp(+i pi j^2 / nfft), divided by m
+ *   d_post  nfft complex64: exp(-i pi k^2 / nfft)
+ * nfft <= 4096 (m <= 8192); the other arguments are those of iqw_stft_c64. */
+int iqw_stft_bluestein_c64(const void* d_x, int64_t n_channels, int64_t n_samples, int64_t x_channel_stride,
+                           const void* d_pre, const void* d_bh, const void* d_post, int32_t nfft, int32_t m,
+                           int64_t hop, int64_t n_frames, int32_t mode, float eps, int32_t bin_lo,
+                           int32_t bin_hi, void* d_out, int64_t out_channel_stride, void* stream);
+/* Longer frames (m = 16384 .. 65536): the same transform composed from three elementwise kernels around two
+ * calls of iqw_stft_c64 (nfft = m, hop = m, all-ones window, complex output) on a (n_frames, m) scratch:
+ *   pre:  a[f][j] = x[f*hop + j] * pre[j] (j < nfft), 0 otherwise      then  A = FFT rows(a)
+ *   mul:  A[f][k] = conj(A[f][k] * bh[k]) in place                      then  r = FFT rows(A)
+ *   post: X[f][k] = post[k] * conj(r[f][k]), k in [bin_lo, bin_hi)  ->  d_out (n_frames, bin_hi - bin_lo) */
+int iqw_bluestein_pre_c64(const void* d_x, int64_t hop, const void* d_pre, int32_t nfft, int32_t m,
+                          int64_t n_frames, void* d_a, void* stream);
+int iqw_bluestein_mul_c64(void* d_a, const void* d_bh, int32_t m, int64_t n_frames, void* stream);
+int iqw_bluestein_post_c64(const void* d_a, const void* d_post, int32_t m, int64_t n_frames, int32_t mode,
+                           float eps, int32_t bin_lo, int32_t bin_hi, void* d_out, void* stream);
+
 /* Kernel 1 with the reducible time statistics fused into its epilogue: persistence spectrum with
  * statistics drawn from {mean, rms, max, peak, min} WITHOUT materialising the spectrogram (8 B per
  * sample of HBM traffic instead of 24).  Replaces fourier.py:1287-1301 (spectrogram, band slice, powtodB)

@@ -48,6 +48,11 @@ SIGNATURES = {
     'iqw_stft_workspace_bytes': (_sz, [_i32, _i64, _i64]),
     'iqw_stft_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i32, _f32,
                                     _i32, _i32, _vp, _i64, _vp, _sz, _vp]),
+    'iqw_stft_bluestein_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i32, _f32,
+                                              _i32, _i32, _vp, _i64, _vp]),
+    'iqw_bluestein_pre_c64': (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _i64, _vp, _vp]),
+    'iqw_bluestein_mul_c64': (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp]),
+    'iqw_bluestein_post_c64': (ctypes.c_int, [_vp, _vp, _i32, _i64, _i32, _f32, _i32, _i32, _vp, _vp]),
     'iqw_stft_reduce_workspace_bytes': (_sz, [_i32]),
     'iqw_stft_reduce_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i32, _f32, _i32, _i32,
                                            ctypes.POINTER(iqw_stat), _i32, _vp, _vp, _sz, _vp]),

@@ -192,6 +192,23 @@ def fir_lowpass_gain(size: int, sample_rate: float, cutoff: float, transition: f
     return (np.fft.fft(taps * sign) * sign).astype(np.complex64)
 
 
+@functools.lru_cache(64)
+def bluestein_tables(window, nfft: int, nzero: int, norm, hop: int):
+    """(pre, bh, post, m) of the chirp-z evaluation of an nfft-point DFT, nfft even and not a power of two
+    (csrc/iqw_stft_bluestein.cu).  Designed in float64; n^2 is reduced mod 2*nfft as an integer so the
+    chirp phase is exact for any length."""
+    c = stft_coefficients(window, nfft, nzero, norm, hop).astype(np.float64)
+    n = np.arange(nfft, dtype=np.int64)
+    ph = (n * n) % (2 * nfft)
+    chirp = np.exp(-1j * np.pi * ph / nfft)                 # exp(-i pi n^2 / N)
+    m = 1 << int(2 * nfft - 2).bit_length()                 # power of two >= 2N - 1
+    b = np.zeros(m, dtype=np.complex128)
+    b[:nfft] = np.conj(chirp)
+    b[m - nfft + 1:] = np.conj(chirp[1:][::-1])             # b[m - j] = b[j]
+    bh = np.fft.fft(b) / m
+    return ((c * chirp).astype(np.complex64), bh.astype(np.complex64), chirp.astype(np.complex64), m)
+
+
 def window_key(window):
     """hashable form of a window argument"""
     if window is None:

@@ -61,6 +61,70 @@ def _device_window(window, nfft: int, nzero: int, norm, hop: int, device) -> tor
     return w
 
 
+_bluestein_cache: dict = {}
+
+
+def _device_bluestein(window, nfft: int, nzero: int, norm, hop: int, device):
+    key = (_plan.window_key(window), nfft, nzero, norm, hop, device.index)
+    with _window_lock:
+        t = _bluestein_cache.get(key)
+        if t is None:
+            pre, bh, post, m = _plan.bluestein_tables(key[0], nfft, nzero, norm, hop)
+            t = _bluestein_cache[key] = (torch.from_numpy(pre).to(device), torch.from_numpy(bh).to(device),
+                                         torch.from_numpy(post).to(device), m)
+    return t
+
+
+BLUESTEIN_SCRATCH_BYTES = 1 << 30        # composed path: frames per pass so that the two scratch rows fit
+
+
+def _stft_bluestein(x2, tables, nfft, hop, f0, nf, mode, eps, bin_lo, bin_hi, out, T, ranged):
+    """frame lengths that are not a power of two (fourier.py:1250-1255 + 200-218): the chirp-z kernel
+    inside one CTA up to nfft 4096, beyond that the same transform composed from three elementwise
+    kernels around two calls of the large power-of-two FFT on a scratch of (frames, m) rows"""
+    pre, bh, post, m = tables
+    C, N = x2.shape
+    nb = bin_hi - bin_lo
+    esz = 8 if mode == _lib.STFT_COMPLEX else 4
+    sp = _stream_ptr(x2.device)
+    if m <= 8192:
+        _lib.check(_lib.lib.iqw_stft_bluestein_c64(
+            ctypes.c_void_p(x2.data_ptr() + f0 * hop * 8), C, (nf - 1) * hop + nfft if ranged else N,
+            x2.stride(0) if C > 1 else N, ctypes.c_void_p(pre.data_ptr()), ctypes.c_void_p(bh.data_ptr()),
+            ctypes.c_void_p(post.data_ptr()), nfft, m, hop, nf, mode, eps, bin_lo, bin_hi,
+            ctypes.c_void_p(out.data_ptr() + f0 * nb * esz), T * nb, sp))
+        return
+    key = (m, x2.device.index)
+    with _window_lock:
+        ones = _ones_cache.get(key)
+        if ones is None:
+            ones = _ones_cache[key] = torch.ones(m, dtype=torch.float32, device=x2.device)
+    chunk = max(1, BLUESTEIN_SCRATCH_BYTES // (2 * m * 8))
+    a = torch.empty((min(chunk, nf), m), dtype=torch.complex64, device=x2.device)
+    b = torch.empty_like(a)
+    ws_bytes = _lib.lib.iqw_stft_workspace_bytes(m, 1, a.shape[0])
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device) if ws_bytes else None
+
+    def rows_fft(src, dst, k):
+        _lib.check(_lib.lib.iqw_stft_c64(
+            ctypes.c_void_p(src.data_ptr()), 1, k * m, k * m, ctypes.c_void_p(ones.data_ptr()), m, m, k,
+            _lib.STFT_COMPLEX, 0.0, 0, m, ctypes.c_void_p(dst.data_ptr()), k * m,
+            ctypes.c_void_p(ws.data_ptr()) if ws_bytes else None, ws_bytes, sp))
+
+    for c in range(C):
+        for g0 in range(f0, f0 + nf, chunk):
+            k = min(chunk, f0 + nf - g0)
+            _lib.check(_lib.lib.iqw_bluestein_pre_c64(
+                ctypes.c_void_p(x2.data_ptr() + (c * x2.stride(0) + g0 * hop) * 8), hop, ctypes.c_void_p(pre.data_ptr()),
+                nfft, m, k, ctypes.c_void_p(a.data_ptr()), sp))
+            rows_fft(a, b, k)
+            _lib.check(_lib.lib.iqw_bluestein_mul_c64(ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(bh.data_ptr()), m, k, sp))
+            rows_fft(b, a, k)
+            _lib.check(_lib.lib.iqw_bluestein_post_c64(
+                ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(post.data_ptr()), m, k, mode, eps, bin_lo, bin_hi,
+                ctypes.c_void_p(out.data_ptr() + ((c * T + g0) * nb) * esz), sp))
+
+
 def _stream_ptr(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -122,7 +186,17 @@ def _stft_device(x2: torch.Tensor, *, window, nfft: int, noverlap: int, nzero: i
     T = _frame_count(N, nfft, noverlap, truncate)
     bin_hi = nfft if bin_hi is None else bin_hi
     nb = bin_hi - bin_lo
-    w = _device_window(window, nfft, nzero, norm, hop, x2.device)
+    pow2 = nfft & (nfft - 1) == 0
+    if pow2:
+        _check_fft_size(nfft, 65536, 'stft')        # before anything is allocated
+        w = _device_window(window, nfft, nzero, norm, hop, x2.device)
+    else:
+        if nfft % 2:
+            raise NotImplementedError('odd frame lengths are not built (the reference multiplies them by a '
+                                      'complex phase-ramp window, fourier.py:139-146)')
+        if 2 * nfft - 1 > 65536:
+            raise NotImplementedError(f'frame length {nfft}: lengths that are not a power of two are built up to 32768')
+        tables = _device_bluestein(window, nfft, nzero, norm, hop, x2.device)
     dtype = torch.complex64 if mode == _lib.STFT_COMPLEX else torch.float32
     if out is None:
         out = torch.empty((C, T, nb), dtype=dtype, device=x2.device)
@@ -137,6 +211,9 @@ def _stft_device(x2: torch.Tensor, *, window, nfft: int, noverlap: int, nzero: i
         return out
     nf = f1 - f0
     esz = 8 if mode == _lib.STFT_COMPLEX else 4
+    if not pow2:
+        _stft_bluestein(x2, tables, nfft, hop, f0, nf, mode, eps, bin_lo, bin_hi, out, T, frames is not None)
+        return out
     ws_bytes = _lib.lib.iqw_stft_workspace_bytes(nfft, C, nf)     # > 0 only for nfft > 8192
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device) if ws_bytes else None
     _lib.check(_lib.lib.iqw_stft_c64(

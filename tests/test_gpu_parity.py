@@ -157,7 +157,9 @@ def test_host_arrays_round_trip(cuda_device):
 def test_unsupported_sizes_fail_loudly(cuda_device):
     x = torch.zeros(1 << 18, dtype=torch.complex64, device=cuda_device)
     with pytest.raises(NotImplementedError):
-        iqw.spectrogram(x, fs=1.0, window='hann', nperseg=1000)
+        iqw.spectrogram(x, fs=1.0, window='hann', nperseg=1001)         # odd: complex phase-ramp window
+    with pytest.raises(NotImplementedError):
+        iqw.spectrogram(x, fs=1.0, window='hann', nperseg=40000)        # not a power of two and > 32768
     with pytest.raises(NotImplementedError):
         iqw.spectrogram(x, fs=1.0, window="hann", nperseg=131072)
     with pytest.raises(NotImplementedError):
@@ -520,3 +522,46 @@ def test_fused_reducible_statistics_host_capture_and_1d(cuda_device):
     devr = iqw.persistence_spectrum(dev_of(x, cuda_device), **args).cpu().numpy()
     assert np.array_equal(host[0], devr[0]) and np.array_equal(host[2], devr[2])
     np.testing.assert_allclose(host[1], devr[1], atol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# frame lengths that are not a power of two (fourier.py:1250-1255: nfft = round(fs / resolution))
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('nfft', [6, 100, 1000, 1536, 3000, 4094, 10000])
+@pytest.mark.parametrize('overlap', [0.0, 0.5])
+def test_any_even_frame_length_vs_oracle(cuda_device, nfft, overlap):
+    nov = int(nfft * overlap)
+    x = synth(nfft + 3, (2, nfft * 11 + 7))
+    for norm in ('power', None):
+        f, t, y = orc.stft(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm=norm)
+        f2, t2, y2 = iqw.stft(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm=norm)
+        assert np.array_equal(f, f2) and np.array_equal(t, t2) and tuple(y2.shape) == y.shape
+        err = np.abs(y2.cpu().numpy() - y) / _tol.complex_tol(y)
+        assert err.max() <= 1.0, (norm, err.max())
+    _, _, ref = orc.spectrogram(x, fs=1e6, window='blackmanharris', nperseg=nfft, noverlap=nov, axis=1)
+    got = iqw.spectrogram(dev_of(x, cuda_device), fs=1e6, window='blackmanharris', nperseg=nfft, noverlap=nov, axis=1,
+                          return_axis_arrays=False).cpu().numpy()
+    assert _tol.power_err_units(got, ref) <= 1.0
+    truth = orc.stft_power_f64(x, window='blackmanharris', nperseg=nfft, noverlap=nov)
+    e_gpu, e_ref = _tol.power_err_units(got, truth), _tol.power_err_units(ref, truth)
+    assert e_gpu <= max(2.0 * e_ref, 0.5), (e_gpu, e_ref)
+    dgot = iqw.spectrogram(dev_of(x, cuda_device), fs=1e6, window='blackmanharris', nperseg=nfft, noverlap=nov, axis=1,
+                           return_axis_arrays=False, dB=True).cpu().numpy()
+    dref = orc.powtodB(ref.copy())
+    assert np.all(np.abs(dgot - dref) <= _tol.db_tol(dref, ref.max(axis=-1, keepdims=True)))
+
+
+@pytest.mark.parametrize('fs,resolution,stats,kw', [
+    (1e6, 1e3, [0.1, 0.5, 0.99, 'mean', 'max'], {}),                      # nfft 1000
+    (100e6, 10e3, [0.5, 'max'], dict(bandwidth=40e6)),                      # nfft 10000, band trim
+    (15.36e6, 10e3, ['median', 'min', 0.9], dict(dB=False)),                # nfft 1536
+])
+def test_persistence_any_frame_length_vs_oracle(cuda_device, fs, resolution, stats, kw):
+    nfft = round(fs / resolution)
+    x = synth(nfft % 71, (2, nfft * 150))
+    args = dict(fs=fs, window='hann', resolution=resolution, fractional_overlap=0.5, statistics=stats, axis=1, **kw)
+    ref = orc.persistence_spectrum(x, **args)
+    got = iqw.persistence_spectrum(dev_of(x, cuda_device), **args)
+    assert tuple(got.shape) == ref.shape
+    _, _, p = orc.spectrogram(x, fs=fs, window='hann', nperseg=nfft, noverlap=nfft // 2, axis=1)
+    _check_persistence(got.cpu().numpy(), ref, stats, x, nfft, kw.get('dB', True), p.max(axis=(1, 2))[:, None])
