@@ -150,8 +150,78 @@ def iq_to_cyclic_power(x, Ts: float, detector_period: float, cyclic_period: floa
 # ---------------------------------------------------------------------------------------------
 # elementwise transforms (power_analysis.py:168-338)
 # ---------------------------------------------------------------------------------------------
+# unit bookkeeping of xarray results (power_analysis.py:39-70): regex substitutions on attrs['units']
+_DB_UNIT_MAPPING = {'dBm': 'mW', 'dBW': 'W', 'dB': 'unitless'}
+
+
+def _unit_sub(prefix_from, prefix_to):
+    import re
+
+    def transform(s: str) -> str:
+        for db_unit, lin_unit in _DB_UNIT_MAPPING.items():
+            s, _ = re.subn('^' + prefix_from(db_unit, lin_unit), prefix_to(db_unit, lin_unit), s, count=1)
+        return s
+    return transform
+
+
+unit_dB_to_linear = _unit_sub(lambda d, l: d, lambda d, l: l)
+unit_linear_to_dB = _unit_sub(lambda d, l: l, lambda d, l: d)
+unit_dB_to_wave = _unit_sub(lambda d, l: d, lambda d, l: '\u221a' + l)
+unit_wave_to_dB = _unit_sub(lambda d, l: '\u221a' + l, lambda d, l: d)
+unit_wave_to_linear = _unit_sub(lambda d, l: '\u221a' + l, lambda d, l: l)
+_UNIT_TRANSFORM = {_lib.EW_POWTODB: unit_linear_to_dB, _lib.EW_DBTOPOW: unit_dB_to_linear,
+                   _lib.EW_ENVTOPOW: unit_wave_to_linear, _lib.EW_ENVTODB: unit_wave_to_dB}
+
+
+def _is_labelled(x) -> bool:
+    """pandas.Series / pandas.DataFrame / xarray.DataArray: objects that wrap an array in `.values`
+    (power_analysis.py:113-118), without importing either package"""
+    return hasattr(x, 'values') and not isinstance(x, (torch.Tensor, dict)) and not hasattr(x, '__cuda_array_interface__') \
+        and type(x).__module__.split('.')[0] in ('pandas', 'xarray')
+
+
+def _repackage_arraylike(values, obj, unit_transform=None):
+    """package `values` into a data type matching `obj` (power_analysis.py:139-165)"""
+    mod = type(obj).__module__.split('.')[0]
+    if mod == 'pandas':
+        import pandas as pd
+        if isinstance(obj, pd.Series):
+            return pd.Series(values, index=obj.index)
+        if isinstance(obj, pd.DataFrame):
+            return pd.DataFrame(values, index=obj.index, columns=obj.columns)
+    elif mod == 'xarray':
+        ret = obj.copy(deep=False, data=values)
+        units = ret.attrs.get('units', None)
+        if units is not None and unit_transform is not None:
+            ret.attrs['units'] = unit_transform(units)
+        return ret
+    raise TypeError(f'unrecognized input type {type(obj)}')
+
+
 def _elementwise(x, op: int, *, use_abs: bool = True, eps: float = 0.0, out=None):
-    """float32 / complex64 array-like -> float32 of the same shape, in the caller's kind"""
+    """float32 / complex64 array-like -> float32 of the same shape, in the caller's kind.  Labelled
+    containers (pandas Series / DataFrame, xarray DataArray) are unwrapped, transformed on the device
+    and re-wrapped with their index / columns / coordinates, as the reference does
+    (power_analysis.py:104-165); host arrays of another real dtype (integers, float64) are computed
+    in float32 on the device and returned in the dtype the reference would return (float64)."""
+    if _is_labelled(x):
+        import numpy as np
+        values = np.asarray(x.values)
+        if out is not None and hasattr(out, 'values'):
+            out = out.values
+        res = _elementwise(values, op, use_abs=use_abs, eps=eps, out=None)
+        if out is not None:
+            out[...] = res
+            res = out
+        return _repackage_arraylike(res, x, _UNIT_TRANSFORM.get(op))
+    if not isinstance(x, (Number, torch.Tensor)) and hasattr(x, 'dtype') and hasattr(x, 'astype'):
+        import numpy as np
+        if isinstance(x, np.ndarray) and x.dtype not in (np.float32, np.complex64):
+            if np.iscomplexobj(x):
+                return _elementwise(x.astype(np.complex64), op, use_abs=use_abs, eps=eps, out=out).astype(np.float64)
+            if x.dtype.kind in 'iubf':
+                wide = np.float64 if x.dtype.itemsize >= 8 or x.dtype.kind in 'iub' else np.float32
+                return _elementwise(x.astype(np.float32), op, use_abs=use_abs, eps=eps, out=out).astype(wide)
     if isinstance(x, Number):            # scalars never touch the device (reference: numexpr)
         if op == _lib.EW_DBTOPOW:
             return 10.0 ** (x / 10.0)

@@ -116,3 +116,28 @@ def test_channelize_power(cc, ov, bins):
         iqw.channelize_power(x, 1e-6, 64, analysis_bins_per_channel=63, window='hann', channel_count=1)
     with pytest.raises(NotImplementedError):
         iqw.channelize_power(x, 1e-6, 64, analysis_bins_per_channel=48, window='hann', axis=1)
+
+
+def test_sigmf_capture_feeds_the_persistence_spectrum(tmp_path, cuda_device):
+    """a SigMF (npy) capture file -> read_sigmf (memory mapped) -> persistence spectrum of
+    every capture segment, equal to the same call on the arrays"""
+    import json
+    import numpy as np
+    import iqwaveform_b200 as iqw
+    from oracle import iqw_oracle as orc
+    from oracle.make_golden import synth
+    n_seg, seg_len = 2, 1 << 16
+    x = synth(9, (n_seg * seg_len,))
+    meta = {'global': {'core:sample_rate': 1e6},
+            'captures': [{'core:sample_start': i * seg_len, 'core:frequency': 1e9 + 1e6 * i,
+                          'core:datetime': f'2024-01-01T00:00:0{i}Z'} for i in range(n_seg)], 'annotations': []}
+    path = tmp_path / 'c.sigmf-meta'
+    path.write_text(json.dumps(meta))
+    np.save(tmp_path / 'c.sigmf-data.npy', x)
+    kw = dict(window='hann', resolution=1e6 / 1024, fractional_overlap=0.5, statistics=[0.5, 'max'], dB=True)
+    freqs, got = iqw.persistence_spectrum_from_sigmf(path, **kw)
+    assert np.array_equal(freqs, [1e9, 1e9 + 1e6]) and got.shape == (2, 2, 1024)
+    want = iqw.persistence_spectrum(x.reshape(n_seg, seg_len), fs=1e6, axis=1, **kw)
+    assert np.array_equal(got, want)
+    ref = orc.persistence_spectrum(x.reshape(n_seg, seg_len), fs=1e6, axis=1, **kw)
+    assert np.abs(got - ref).max() < 1e-3

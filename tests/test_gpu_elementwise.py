@@ -136,3 +136,48 @@ def test_input_domains(cuda_device):
     for d in ('rms', 'peak'):
         for k in ('min', 'mean', 'max'):
             np.testing.assert_allclose(got[d][k].cpu().numpy(), want[d][k], rtol=3e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# labelled containers (power_analysis.py:104-165) -- includes the reference's own tests
+# (/root/reference/tests/test_transforms.py:1-17) run against the product
+# ---------------------------------------------------------------------------------------------
+def test_reference_test_transforms(cuda_device):
+    import pandas as pd
+    from iqwaveform_b200 import powtodB
+    assert powtodB(1) == 0                      # test_transform_int
+    assert powtodB(1.0) == 0                    # test_transform_float
+    s = pd.Series([1, 10, 100])                 # test_transform_series
+    ret = powtodB(s)
+    assert isinstance(ret, pd.Series) and ret.index.equals(s.index)
+    assert np.allclose(pd.Series([0, 10, 20]).values, ret.values)
+
+
+def test_pandas_in_pandas_out(cuda_device):
+    import pandas as pd
+    from iqwaveform_b200 import dBtopow, envtodB, envtopow, powtodB
+    rng = np.random.default_rng(0)
+    idx = pd.Index(np.arange(50) * 0.25, name='t')
+    df = pd.DataFrame(rng.random((50, 3)).astype(np.float32) + 0.1, index=idx, columns=['a', 'b', 'c'])
+    out = powtodB(df)
+    assert isinstance(out, pd.DataFrame) and out.index.equals(idx) and list(out.columns) == ['a', 'b', 'c']
+    np.testing.assert_allclose(out.values, orc.powtodB(df.values.copy()), atol=5e-5)
+    back = dBtopow(out)
+    assert isinstance(back, pd.DataFrame)
+    np.testing.assert_allclose(back.values, df.values, rtol=2e-5)
+    z = pd.Series((rng.standard_normal(40) + 1j * rng.standard_normal(40)).astype(np.complex64))
+    p = envtopow(z)
+    assert isinstance(p, pd.Series) and p.dtype == np.float32
+    np.testing.assert_allclose(p.values, np.abs(z.values) ** 2, rtol=1e-6)
+    d = envtodB(z)
+    np.testing.assert_allclose(d.values, 20 * np.log10(np.abs(z.values)), atol=5e-5)
+    # float64 / integer host arrays: computed in float32, returned in the reference's dtype
+    y = powtodB(np.array([1.0, 100.0]))
+    assert y.dtype == np.float64 and np.allclose(y, [0, 20], atol=1e-5)
+
+
+def test_unit_transforms_match_the_reference_strings():
+    from iqwaveform_b200 import power_analysis as P
+    assert P.unit_linear_to_dB('mW') == 'dBm' and P.unit_dB_to_linear('dBW/Hz') == 'W/Hz'
+    assert P.unit_wave_to_dB('√mW') == 'dBm' and P.unit_wave_to_linear('√W') == 'W'
+    assert P.unit_dB_to_wave('dBm') == '√mW'
