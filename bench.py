@@ -250,6 +250,15 @@ def extra_configs(torch, iqw, dev, peak):
                      'algorithmic_bytes_per_sample': bps, 'algorithmic_GBps': round(gbs, 1),
                      'frac_of_measured_hbm_peak': round(gbs / peak, 4)})
 
+    # configs[0]: the reference's own CPU-runnable case, plain call and as one captured CUDA graph
+    n = 15_360_000
+    x = device_capture(torch, n, 1, dev).view(1, n)
+    kw0 = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5, statistics=[0.5, 0.99], dB=True, axis=1)
+    row('configs[0] persistence_spectrum 15.36 MS/s x 1 s, nfft 1024 hann 50 %, q = [0.5, 0.99]', n,
+        _timed(torch, lambda: iqw.persistence_spectrum(x, **kw0), reps=5), 24)
+    g = iqw.GraphedCall(iqw.persistence_spectrum, x, **kw0)
+    row('configs[0] same call replayed as one CUDA graph (iqw.GraphedCall)', n, _timed(torch, lambda: g(), reps=5), 24)
+    del x, g
     # configs[1]: stft/spectrogram, 100 MS/s x 10 s, nfft 2048 Blackman-Harris, 50 % overlap, dB
     n = 1_000_000_000
     x = device_capture(torch, n, 2, dev)

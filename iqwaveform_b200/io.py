@@ -111,7 +111,7 @@ def persistence_spectrum_from_sigmf(metadata_path: str, *, window, resolution: f
     fs = 1.0 / Ts
     rows = []
     for seg in segments:
-        seg = np.ascontiguousarray(seg, dtype=np.complex64)
+        seg = np.array(seg, dtype=np.complex64)       # out of the (read-only) file mapping
         rows.append(fourier.persistence_spectrum(seg, fs=fs, window=window, resolution=resolution,
                                                  fractional_overlap=fractional_overlap, statistics=statistics,
                                                  dB=dB, axis=0, **kw))

@@ -141,3 +141,21 @@ def test_sigmf_capture_feeds_the_persistence_spectrum(tmp_path, cuda_device):
     assert np.array_equal(got, want)
     ref = orc.persistence_spectrum(x.reshape(n_seg, seg_len), fs=1e6, axis=1, **kw)
     assert np.abs(got - ref).max() < 1e-3
+
+
+def test_graphed_call_replays_the_same_bits(cuda_device):
+    """small problems: the whole persistence-spectrum call captured once as a CUDA graph and replayed on
+    new data gives the bits of the plain call"""
+    import torch
+    import iqwaveform_b200 as iqw
+    from oracle.make_golden import synth
+    kw = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5, statistics=[0.5, 0.99, 'max'],
+              dB=True, axis=1)
+    a = torch.from_numpy(synth(1, (1, 1 << 21))).to(cuda_device)
+    b = torch.from_numpy(synth(2, (1, 1 << 21))).to(cuda_device)
+    g = iqw.GraphedCall(iqw.persistence_spectrum, a, **kw)
+    assert torch.equal(g(), iqw.persistence_spectrum(a, **kw))
+    assert torch.equal(g(b), iqw.persistence_spectrum(b, **kw))
+    assert torch.equal(g(a), iqw.persistence_spectrum(a, **kw))
+    with pytest.raises(TypeError):
+        iqw.GraphedCall(iqw.persistence_spectrum, a.cpu(), **kw)

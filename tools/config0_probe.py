@@ -1,23 +1,24 @@
-#!/usr/bin/env python
-"""per-kernel times of BASELINE configs[0] (15.36 MS/s x 1 s, nfft 1024, q = [0.5, 0.99]): a small,
-launch-bound problem.  python tools/config0_probe.py"""
-import os, sys
+"""probe: BASELINE configs[0] (persistence spectrum of 15.36 M samples, nfft 1024, q = [0.5, 0.99]) --
+plain call against the captured CUDA graph, with the per-kernel times of the plain call"""
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 import iqwaveform_b200 as iqw
 from iqwaveform_b200 import _lib
-
+dev = torch.device('cuda:0')
 n = 15_360_000
-x = bench.device_capture(torch, n, 1, torch.device('cuda', 0)).view(1, n)
+x = bench.device_capture(torch, n, 1, dev).view(1, n)
 kw = dict(fs=15.36e6, window='hann', resolution=15e3, fractional_overlap=0.5, statistics=[0.5, 0.99], dB=True, axis=1)
-for it in range(3):
-    _lib.profile(it == 2, fine=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out = iqw.persistence_spectrum(x, **kw); e1.record(); torch.cuda.synchronize()
-    print(f'call {it}: {e0.elapsed_time(e1):.3f} ms')
-rep = _lib.profile_report()
-tot = sum(ms for _, ms in rep.values())
-for k, (c, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
-    print(f'  {k:24s} {c:3d} launches {ms * 1e3:8.1f} us')
-print(f'  sum of kernels {tot * 1e3:.1f} us')
+plain = bench._timed(torch, lambda: iqw.persistence_spectrum(x, **kw), reps=10)
+_lib.profile(True, fine=True)
+ref = iqw.persistence_spectrum(x, **kw).clone()
+torch.cuda.synchronize()
+rep = _lib.profile_report(); _lib.profile(False)
+print('plain call %.4f ms; kernels: %s' % (plain, ', '.join(f'{k} {c}x {ms:.4f}' for k, (c, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]))))
+print('sum of kernel times %.4f ms over %d launches' % (sum(ms for c, ms in rep.values()), sum(c for c, ms in rep.values())))
+g = iqw.GraphedCall(iqw.persistence_spectrum, x, **kw)
+graphed = bench._timed(torch, lambda: g(), reps=10)
+with_copy = bench._timed(torch, lambda: g(x), reps=10)
+print('graph replay %.4f ms (%.1f GS/s, %.3f of the measured HBM peak at 24 B/sample); with the input copy %.4f ms; identical: %s'
+      % (graphed, n / graphed / 1e6, 24 * n / graphed / 1e6 / bench.measured_peak()[0], with_copy, bool(torch.equal(g(), ref))))
