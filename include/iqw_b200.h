@@ -317,7 +317,10 @@ int iqw_debug_set_stft_scratch_cap(size_t bytes);
  * kernel, csrc/iqw_stft2p.cu: 32 / 64 values per thread, one shared-memory exchange per frame, frames
  * staged by bulk copies (TMA) when every frame start is 16-byte aligned), 1 = always the three-pass kernel
  * (csrc/iqw_stft.cu: 16 values per thread, two exchanges), 2 = two-pass with plain global loads, 3 = two-pass
- * staged (same as 0).  All compute the same transform; results differ by float32 rounding only. */
+ * staged (same as 0).  The same switch serves nfft 8192 .. 65536: 0 = the one-pass kernel that keeps the frame
+ * in (distributed) shared memory, a thread-block cluster of 2 / 4 CTAs at nfft 32768 / 65536
+ * (csrc/iqw_stft3p.cu), 1 = the three-pass kernel (8192) / the two-kernel four-step path through the
+ * workspace (16384 .. 65536).  All compute the same transform; results differ by float32 rounding only. */
 int iqw_debug_set_stft_variant(int variant);
 
 /* Test aid: width of the brackets the row sample puts around each target rank on the long-column

@@ -381,7 +381,11 @@ extern "C" size_t iqw_stft_workspace_bytes(int32_t nfft, int64_t n_channels, int
     if (nfft < 2 || (nfft & (nfft - 1))) return 0;
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
-    return stft_large_workspace_bytes(log2n, n_channels, n_frames);
+    // the four-step path's scratch (also the fallback for unaligned captures) or the cluster kernels' exchange
+    // scratch, whichever is larger
+    const size_t four_step = stft_large_workspace_bytes(log2n, n_channels, n_frames);
+    const size_t cluster = stft_three_pass_scratch_bytes(log2n, n_channels, n_frames);
+    return four_step > cluster ? four_step : cluster;
 }
 
 extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_samples,
@@ -425,6 +429,13 @@ extern "C" int iqw_stft_c64(const void* d_x, int64_t n_channels, int64_t n_sampl
     a.bin_hi = bin_hi;
     a.out = d_out;
     a.out_ch_stride = out_channel_stride;
+    // nfft 8192 / 16384: the one-pass kernel with the frame in one CTA's shared memory.  nfft 32768 / 65536: the
+    // cluster variant of that kernel is built and correct but measured no faster than the four-step path
+    // (18 % / 15 % against 19 % of the HBM peak: its exchanges, through DSMEM or through the L2, are not overlapped
+    // with arithmetic at one frame per cluster), so it runs only on request (variant 3)
+    if (stft_variant() != 1 && stft_three_pass_cluster_ok(a, log2n) &&
+        (log2n < 15 || (stft_variant() == 3 && d_workspace && workspace_bytes >= stft_three_pass_scratch_bytes(log2n, 1, 1))))
+        return launch_stft_three_pass_cluster(a, log2n, mode, d_workspace, workspace_bytes, s);
     if (log2n > 13) return launch_stft_large(a, log2n, mode, d_workspace, workspace_bytes, s);
     if (stft_two_pass_wanted(log2n)) return launch_stft_two_pass(a, log2n, mode, s);
     if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;

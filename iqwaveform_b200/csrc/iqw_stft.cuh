@@ -26,6 +26,7 @@ struct StftArgs {
     double* part_sum;          // sum of the power, or of its dB when reduce_dB
     int reduce_dB;
     int reduce_flags;          // bit 0: max / min wanted, bit 1: sum wanted
+    float2* xscratch;          // cluster kernels (nfft 32768 / 65536): per-cluster exchange scratch in global memory
 };
 
 constexpr int kStftReduce = 3;   // internal mode of stft_kernel, next to IQW_STFT_COMPLEX / POWER / DB
@@ -84,6 +85,13 @@ int get_twiddles(int log2n, cudaStream_t stream, const float2** out);
 // nfft 1024 / 2048 / 4096, two-pass geometry (iqw_stft2p.cu)
 bool stft_two_pass_wanted(int log2n);
 int launch_stft_two_pass(const StftArgs& a, int log2n, int mode, cudaStream_t stream);
+
+// nfft 8192 .. 65536 in one pass: frame in (distributed) shared memory, cluster of 1 / 1 / 2 / 4 CTAs (iqw_stft3p.cu)
+bool stft_three_pass_cluster_ok(const StftArgs& a, int log2n);
+size_t stft_three_pass_scratch_bytes(int log2n, long long n_channels, long long n_frames);
+int launch_stft_three_pass_cluster(const StftArgs& a, int log2n, int mode, void* workspace, size_t workspace_bytes,
+                                   cudaStream_t stream);
+int stft_variant();      // iqw_debug_set_stft_variant
 
 // nfft = 2^14 .. 2^16 (iqw_stft_large.cu)
 size_t stft_large_workspace_bytes(int log2n, long long n_channels, long long n_frames);

@@ -328,6 +328,8 @@ static int launch2p(const StftArgs& a, int mode, cudaStream_t s) {
     return fail(IQW_ERR_INVALID, "unknown stft mode %d", mode);
 }
 
+int stft_variant() { return g_stft_variant.load(); }
+
 bool stft_two_pass_wanted(int log2n) {
     if (log2n < 10 || log2n > 12) return false;
     return g_stft_variant.load() != 1;

@@ -565,3 +565,25 @@ def test_persistence_any_frame_length_vs_oracle(cuda_device, fs, resolution, sta
     assert tuple(got.shape) == ref.shape
     _, _, p = orc.spectrogram(x, fs=fs, window='hann', nperseg=nfft, noverlap=nfft // 2, axis=1)
     _check_persistence(got.cpu().numpy(), ref, stats, x, nfft, kw.get('dB', True), p.max(axis=(1, 2))[:, None])
+
+
+@pytest.mark.parametrize('nfft,nov', [(32768, 16384), (65536, 49152), (8192, 4096), (16384, 0)])
+def test_cluster_kernel_on_request_vs_oracle(cuda_device, nfft, nov):
+    """variant 3 at nfft 32768 / 65536: one frame per thread-block cluster of 2 / 4 CTAs, samples staged by bulk
+    copies, exchanges through an L2-resident scratch ordered by barrier.cluster; variant 1 at 8192 / 16384: the
+    older kernels those sizes used before.  Same transform as the default path."""
+    from iqwaveform_b200 import _lib
+    x = synth(nfft % 97, (2, nfft * 7 + 11))
+    _, _, ref = orc.stft(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm='power')
+    _, _, pref = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1)
+    try:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(3 if nfft >= 32768 else 1))
+        y = iqw.stft(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1,
+                     norm='power', return_axis_arrays=False).cpu().numpy()
+        p = iqw.spectrogram(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1,
+                            return_axis_arrays=False, dB=True).cpu().numpy()
+    finally:
+        _lib.check(_lib.lib.iqw_debug_set_stft_variant(0))
+    assert (np.abs(y - ref) / _tol.complex_tol(ref)).max() <= 1.0
+    dref = orc.powtodB(pref.copy())
+    assert np.all(np.abs(p - dref) <= _tol.db_tol(dref, pref.max(axis=-1, keepdims=True)))
