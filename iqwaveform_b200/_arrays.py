@@ -26,6 +26,15 @@ class Residence:
         return host.numpy() if self.kind == 'numpy' else host
 
 
+def from_numpy_readonly_ok(a: np.ndarray) -> torch.Tensor:
+    """torch.from_numpy without the warning about read-only arrays (memory-mapped captures): the tensor is
+    only ever the SOURCE of a host->device copy"""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', UserWarning)
+        return torch.from_numpy(a)
+
+
 def _device() -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError('iqwaveform_b200 needs a CUDA device (there is no CPU fallback)')
@@ -42,7 +51,7 @@ def to_device(x) -> tuple[torch.Tensor, Residence]:
         return src.to(dev, non_blocking=True), Residence('torch_cpu')
     if isinstance(x, np.ndarray):
         dev = _device()
-        return torch.from_numpy(np.ascontiguousarray(x)).to(dev, non_blocking=True), Residence('numpy')
+        return from_numpy_readonly_ok(np.ascontiguousarray(x)).to(dev, non_blocking=True), Residence('numpy')
     if hasattr(x, '__dlpack__'):
         t = torch.from_dlpack(x)
         if not t.is_cuda:

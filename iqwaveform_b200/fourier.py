@@ -805,7 +805,7 @@ def _host_rows(x, axis):
     """(rows tensor (C, N) on the host with contiguous rows, kind, squeeze) for a host capture whose
     time axis is the last one, else None"""
     if isinstance(x, np.ndarray):
-        kind, t = 'numpy', (torch.from_numpy(x) if x.dtype == np.complex64 else None)
+        kind, t = 'numpy', (_arrays.from_numpy_readonly_ok(x) if x.dtype == np.complex64 else None)
     elif isinstance(x, torch.Tensor) and not x.is_cuda:
         kind, t = 'torch_cpu', (x if x.dtype == torch.complex64 else None)
     else:
