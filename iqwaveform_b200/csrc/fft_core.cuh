@@ -128,6 +128,37 @@ IQW_HD float2 cmul(float2 a, float2 b) {
 }
 IQW_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 #endif
+// fused forms used where a scaling meets the first radix-2 stage of a butterfly: one rounding less per value
+#if defined(__CUDA_ARCH__) && defined(IQW_PACKED_F32X2)
+IQW_HD float2 cfma_rs(float2 a, float s, float2 c) {     // a * s + c, s real: one FFMA2
+    float2 d;
+    asm("{ .reg .b64 pa, ss, pc; mov.b64 pa, {%2, %3}; mov.b64 ss, {%4, %4}; mov.b64 pc, {%5, %6}; "
+        "fma.rn.f32x2 pa, pa, ss, pc; mov.b64 {%0, %1}, pa; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+    return d;
+}
+IQW_HD float2 cfma(float2 a, float2 b, float2 c) {       // a * b + c, all complex: two FFMA2
+    float2 d;
+    asm("{ .reg .b64 pa, pas, cc, sm, p; .reg .f32 ns; mov.b64 pa, {%2, %3}; mov.b64 pas, {%3, %2}; "
+        "mov.b64 cc, {%4, %4}; neg.f32 ns, %5; mov.b64 sm, {ns, %5}; mov.b64 p, {%6, %7}; "
+        "fma.rn.f32x2 p, pa, cc, p; fma.rn.f32x2 p, pas, sm, p; mov.b64 {%0, %1}, p; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+IQW_HD float2 ctwice_minus(float2 u, float2 s) {         // 2u - s: one FFMA2
+    float2 d;
+    asm("{ .reg .b64 pu, two, ps; .reg .f32 nx, ny; mov.b64 pu, {%2, %3}; mov.b64 two, {0f40000000, 0f40000000}; "
+        "neg.f32 nx, %4; neg.f32 ny, %5; mov.b64 ps, {nx, ny}; fma.rn.f32x2 pu, pu, two, ps; mov.b64 {%0, %1}, pu; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(u.x), "f"(u.y), "f"(s.x), "f"(s.y));
+    return d;
+}
+#else
+IQW_HD float2 cfma_rs(float2 a, float s, float2 c) { return make_float2(a.x * s + c.x, a.y * s + c.y); }
+IQW_HD float2 cfma(float2 a, float2 b, float2 c) {
+    return make_float2(a.x * b.x - a.y * b.y + c.x, a.x * b.y + a.y * b.x + c.y);
+}
+IQW_HD float2 ctwice_minus(float2 u, float2 s) { return make_float2(2.f * u.x - s.x, 2.f * u.y - s.y); }
+#endif
 IQW_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }          // a * (-i)
 // a * exp(-i*pi/4)  and  a * exp(-3i*pi/4)
 #if defined(__CUDA_ARCH__) && defined(IQW_PACKED_F32X2)
@@ -172,15 +203,12 @@ IQW_HD void bfly4(float2* a) {
     a[3 * S] = csub(t1, t3);
 }
 
+// second half of the radix-8 butterfly: sums s_n = a_n + a_{n+4} and differences d_n = a_n - a_{n+4} in,
+// X[2k] = DFT4(s), X[2k+1] = DFT4(d_n W8^n) out (decimation in frequency)
 template <int S>
-IQW_HD void bfly8(float2* a) {
-    // decimation in frequency: X[2k] = DFT4(a_n + a_{n+4}), X[2k+1] = DFT4((a_n - a_{n+4}) W8^n)
-    float2 s0 = cadd(a[0], a[4 * S]), d0 = csub(a[0], a[4 * S]);
-    float2 s1 = cadd(a[S], a[5 * S]), d1 = mul_w8_1(csub(a[S], a[5 * S]));
-    float2 s2 = cadd(a[2 * S], a[6 * S]), d2 = mul_mi(csub(a[2 * S], a[6 * S]));
-    float2 s3 = cadd(a[3 * S], a[7 * S]), d3 = mul_w8_3(csub(a[3 * S], a[7 * S]));
+IQW_HD void bfly8_tail(float2* a, float2 s0, float2 s1, float2 s2, float2 s3, float2 d0, float2 d1, float2 d2, float2 d3) {
     float2 e[4] = {s0, s1, s2, s3};
-    float2 o[4] = {d0, d1, d2, d3};
+    float2 o[4] = {d0, mul_w8_1(d1), mul_mi(d2), mul_w8_3(d3)};
     bfly4<1>(e);
     bfly4<1>(o);
 #pragma unroll
@@ -188,6 +216,64 @@ IQW_HD void bfly8(float2* a) {
         a[(2 * k) * S] = e[k];
         a[(2 * k + 1) * S] = o[k];
     }
+}
+
+template <int S>
+IQW_HD void bfly8(float2* a) {
+    bfly8_tail<S>(a, cadd(a[0], a[4 * S]), cadd(a[S], a[5 * S]), cadd(a[2 * S], a[6 * S]), cadd(a[3 * S], a[7 * S]),
+                  csub(a[0], a[4 * S]), csub(a[S], a[5 * S]), csub(a[2 * S], a[6 * S]), csub(a[3 * S], a[7 * S]));
+}
+
+// radix-8 butterfly of a[n*S] * w[n*S] (w real: the window): the scaling rides on the first radix-2 stage,
+// u = a_n w_n, s = a_{n+4} w_{n+4} + u, d = -a_{n+4} w_{n+4} + u: 12 packed instructions instead of 16
+template <int S>
+IQW_HD void bfly8_scaled(float2* a, const float* w) {
+    float2 sv[4], dv[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const float2 u = cscale(a[n * S], w[n * S]);
+        sv[n] = cfma_rs(a[(n + 4) * S], w[(n + 4) * S], u);
+        dv[n] = cfma_rs(a[(n + 4) * S], -w[(n + 4) * S], u);
+    }
+    bfly8_tail<S>(a, sv[0], sv[1], sv[2], sv[3], dv[0], dv[1], dv[2], dv[3]);
+}
+// radix-8 butterfly of a[n*S] * t[n] (t complex twiddles; t[0] is 1 when FIRST_ONE): u = a_n t_n,
+// s = a_{n+4} t_{n+4} + u (two FFMA2), d = 2u - s (one): 5 packed instructions per pair instead of 6
+template <int S, bool FIRST_ONE>
+IQW_HD void bfly8_twiddled(float2* a, const float2* t) {
+    float2 sv[4], dv[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const float2 u = (FIRST_ONE && n == 0) ? a[0] : cmul(a[n * S], t[n]);
+        sv[n] = cfma(a[(n + 4) * S], t[n + 4], u);
+        dv[n] = ctwice_minus(u, sv[n]);
+    }
+    bfly8_tail<S>(a, sv[0], sv[1], sv[2], sv[3], dv[0], dv[1], dv[2], dv[3]);
+}
+// the same for the radix-4 first stage of the 32-point transform (pairs n, n+2)
+template <int S>
+IQW_HD void bfly4_tail(float2* a, float2 t0, float2 t2, float2 t1, float2 d13) {
+    // t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, d13 = a1 - a3
+    const float2 t3 = mul_mi(d13);
+    a[0] = cadd(t0, t2);
+    a[S] = cadd(t1, t3);
+    a[2 * S] = csub(t0, t2);
+    a[3 * S] = csub(t1, t3);
+}
+template <int S>
+IQW_HD void bfly4_scaled(float2* a, const float* w) {
+    const float2 u0 = cscale(a[0], w[0]), u1 = cscale(a[S], w[S]);
+    const float2 t0 = cfma_rs(a[2 * S], w[2 * S], u0), t1 = cfma_rs(a[2 * S], -w[2 * S], u0);
+    const float2 t2 = cfma_rs(a[3 * S], w[3 * S], u1), d13 = cfma_rs(a[3 * S], -w[3 * S], u1);
+    bfly4_tail<S>(a, t0, t2, t1, d13);
+}
+template <int S, bool FIRST_ONE>
+IQW_HD void bfly4_twiddled(float2* a, const float2* t) {
+    const float2 u0 = FIRST_ONE ? a[0] : cmul(a[0], t[0]);
+    const float2 u1 = cmul(a[S], t[1]);
+    const float2 t0 = cfma(a[2 * S], t[2], u0), t1 = ctwice_minus(u0, t0);
+    const float2 t2 = cfma(a[3 * S], t[3], u1), d13 = ctwice_minus(u1, t2);
+    bfly4_tail<S>(a, t0, t2, t1, d13);
 }
 
 template <int S>
@@ -338,9 +424,14 @@ IQW_HD float2 mul_w64(float2 a, int m) {
 
 // 64-point forward DFT in place, natural order in and out.  r = 8a + b, k = c + 8d:
 // W64^(rk) = W8^(ac) W64^(bc) W8^(bd)
+// everything after the first stage (a[8c + b] = y[b][c]): internal twiddles, second stage, natural order
+IQW_HD void bfly64_tail(float2* a);
 IQW_HD void bfly64(float2* a) {
 #pragma unroll
     for (int b = 0; b < 8; ++b) bfly8<8>(a + b);                 // a[8c + b] = y[b][c]
+    bfly64_tail(a);
+}
+IQW_HD void bfly64_tail(float2* a) {
 #pragma unroll
     for (int b = 1; b < 8; ++b)
 #pragma unroll
@@ -355,9 +446,13 @@ IQW_HD void bfly64(float2* a) {
 }
 
 // 32-point forward DFT in place.  r = 8a + b (a < 4), k = c + 4d (c < 4): W32^(rk) = W4^(ac) W32^(bc) W8^(bd)
+IQW_HD void bfly32_tail(float2* a);
 IQW_HD void bfly32(float2* a) {
 #pragma unroll
     for (int b = 0; b < 8; ++b) bfly4<8>(a + b);                 // a[8c + b] = y[b][c], c < 4
+    bfly32_tail(a);
+}
+IQW_HD void bfly32_tail(float2* a) {
 #pragma unroll
     for (int b = 1; b < 8; ++b)
 #pragma unroll
@@ -375,6 +470,38 @@ template <int R>
 IQW_HD void bfly_big(float2* a) {
     if constexpr (R == 64) bfly64(a);
     else bfly32(a);
+}
+// a[r] * w[r] (real scales, the window) -> DFT, the scaling fused into the first stage
+template <int R>
+IQW_HD void bfly_big_scaled(float2* a, const float* w) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if constexpr (R == 64) bfly8_scaled<8>(a + b, w + b);
+        else bfly4_scaled<8>(a + b, w + b);
+    }
+    if constexpr (R == 64) bfly64_tail(a);
+    else bfly32_tail(a);
+}
+// a[8k + b] * A[k] * B[b] (A[0] = B[0] = 1 implied) -> DFT: the pass-B twiddles of the two-pass kernels,
+// products formed per first-stage butterfly and fused into it
+template <int R>
+IQW_HD void bfly_big_twiddled(float2* a, const float2* A, const float2* B) {
+    constexpr int NK = R / 8;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        float2 t[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) t[k] = k == 0 ? B[b] : (b == 0 ? A[k] : cmul(A[k], B[b]));
+        if constexpr (R == 64) {
+            if (b == 0) bfly8_twiddled<8, true>(a + b, t);
+            else bfly8_twiddled<8, false>(a + b, t);
+        } else {
+            if (b == 0) bfly4_twiddled<8, true>(a + b, t);
+            else bfly4_twiddled<8, false>(a + b, t);
+        }
+    }
+    if constexpr (R == 64) bfly64_tail(a);
+    else bfly32_tail(a);
 }
 
 }  // namespace iqw

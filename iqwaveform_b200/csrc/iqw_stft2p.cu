@@ -144,22 +144,23 @@ stft2p_kernel(const StftArgs a) {
 
     for (; f < f_end; ++f) {
         float2 v[E];
-        if constexpr (STAGED) {
+        {
+            // the window multiply rides on the first radix-2 stage of the butterfly (bfly_big_scaled)
             float w[RA];
 #pragma unroll
             for (int r = 0; r < RA; ++r) w[r] = __ldg(wp + r * RB);
-            mbar_wait(&full_bar[slot], parity);
-            parity ^= 1;
+            if constexpr (STAGED) {
+                mbar_wait(&full_bar[slot], parity);
+                parity ^= 1;
 #pragma unroll
-            for (int r = 0; r < RA; ++r) v[r] = cscale(buf[ltid + r * RB], w[r]);
-        } else {
-            const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
+                for (int r = 0; r < RA; ++r) v[r] = buf[ltid + r * RB];
+            } else {
+                const float2* src = a.x + c * a.x_ch_stride + frame * a.hop + ltid;
 #pragma unroll
-            for (int r = 0; r < RA; ++r) v[r] = ldg_stream(src + r * RB);
-#pragma unroll
-            for (int r = 0; r < RA; ++r) v[r] = cscale(v[r], __ldg(wp + r * RB));
+                for (int r = 0; r < RA; ++r) v[r] = ldg_stream(src + r * RB);
+            }
+            bfly_big_scaled<RA>(v, w);
         }
-        bfly_big<RA>(v);
 
         slot_sync();                             // every thread of the slot has read the previous frame's M
         {
@@ -191,21 +192,15 @@ stft2p_kernel(const StftArgs a) {
         for (int q = 0; q < NB; ++q) {
             const int jB = ltid + q * TPF;
             float2* u = v + q * RB;
-            float2 A[C::NA8];
+            // pass-B twiddles A_k * B_b, products formed per first-stage butterfly and fused into it
+            float2 A[C::NA8], B[8];
+            A[0] = make_float2(1.f, 0.f);
+            B[0] = make_float2(1.f, 0.f);
 #pragma unroll
             for (int k = 1; k < C::NA8; ++k) A[k] = tw[(k - 1) * RA + jB];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                float2 B = make_float2(1.f, 0.f);
-                if (b > 0) B = tw[(C::NA8 - 1 + b - 1) * RA + jB];
-#pragma unroll
-                for (int k = 0; k < C::NA8; ++k) {
-                    if (k == 0 && b == 0) continue;
-                    const float2 t = k == 0 ? B : (b == 0 ? A[k] : cmul(A[k], B));
-                    u[8 * k + b] = cmul(u[8 * k + b], t);
-                }
-            }
-            bfly_big<RB>(u);
+            for (int b = 1; b < 8; ++b) B[b] = tw[(C::NA8 - 1 + b - 1) * RA + jB];
+            bfly_big_twiddled<RB>(u, A, B);
         }
 
         const long long row0 = c_cur * a.out_ch_stride + frame_cur * (long long)nbins - a.bin_lo;
