@@ -177,7 +177,8 @@ stft3p_kernel(const StftArgs a) {
             s3_mbar_wait(&full_bar[slot], parity);
             parity ^= 1;
 #pragma unroll
-            for (int r = 0; r < 64; ++r) v[r] = cscale(buf[r * TPC + lt], w[r]);
+            for (int r = 0; r < 64; ++r) v[r] = buf[r * TPC + lt];
+            bfly_big_scaled<64>(v, w);                   // window fused into the first radix-2 stage; v[k] = element 64*gt + k
         }
         const long long c_cur = c, frame_cur = frame;
         if (++frame == a.n_frames) { frame = 0; ++c; }
@@ -189,7 +190,6 @@ stft3p_kernel(const StftArgs a) {
                 stage(a.x + c * a.x_ch_stride + frame * a.hop);
             }
         }
-        bfly64(v);                                       // v[k] = element 64*gt + k
 
         if constexpr (NC == 1) {
             slot_sync();                                 // 1: every thread of the frame has read its samples
@@ -210,24 +210,18 @@ stft3p_kernel(const StftArgs a) {
             for (int r = 0; r < 64; ++r) v[r] = __ldcg(x1 + (size_t)(r * R3 + h) * SEG + l);
         }
 
-        // pass B: W_4096^(r*l), r = 8k + b, factored A_k * B_b (table of the two-pass kernel at nfft 4096)
+        // pass B: W_4096^(r*l), r = 8k + b, factored A_k * B_b (table of the two-pass kernel at nfft 4096), the
+        // products formed per first-stage butterfly and fused into it
         {
-            float2 A[8];
+            float2 A[8], B[8];
+            A[0] = make_float2(1.f, 0.f);
+            B[0] = make_float2(1.f, 0.f);
 #pragma unroll
             for (int k = 1; k < 8; ++k) A[k] = tw[(k - 1) * 64 + l];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                float2 B = make_float2(1.f, 0.f);
-                if (b > 0) B = tw[(7 + b - 1) * 64 + l];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (k == 0 && b == 0) continue;
-                    const float2 t = k == 0 ? B : (b == 0 ? A[k] : cmul(A[k], B));
-                    v[8 * k + b] = cmul(v[8 * k + b], t);
-                }
-            }
+            for (int b = 1; b < 8; ++b) B[b] = tw[(7 + b - 1) * 64 + l];
+            bfly_big_twiddled<64>(v, A, B);              // v[r] = element h*4096 + l + 64*r
         }
-        bfly64(v);                                       // v[r] = element h*4096 + l + 64*r
 
         // exchange 2: element r goes to thread 64*(r mod R3) + l of the frame, slot (r / R3)*R3 + h
         if constexpr (NC == 1) {
