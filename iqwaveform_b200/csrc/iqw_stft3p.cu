@@ -42,7 +42,10 @@ struct P3Cfg {
     static constexpr int TPF = N / 64;                   // threads per frame
     static constexpr int TPC = TPF < 256 ? TPF : 256;    // threads of one frame inside one CTA
     static constexpr int NC = TPF / TPC;                 // CTAs per frame (cluster size): 1, 2, 4, 8
-    static constexpr int SLOTS = NC == 1 ? (TPC == 128 ? 3 : 1) : 1;    // frame slots per CTA
+#ifndef IQW_P3_SLOTS13
+#define IQW_P3_SLOTS13 3
+#endif
+    static constexpr int SLOTS = NC == 1 ? (TPC == 128 ? IQW_P3_SLOTS13 : 1) : 1;    // frame slots per CTA
     static constexpr int THREADS = SLOTS * TPC;          // 384, or 128 with three CTAs per SM
     static constexpr int MIN_BLOCKS = (NC > 1 && TPC == 128) ? 3 : 1;
     static constexpr int HL = R3 / NC;                   // groups of 64 threads per CTA and slot (2 or 4)

@@ -587,3 +587,26 @@ def test_cluster_kernel_on_request_vs_oracle(cuda_device, nfft, nov):
     assert (np.abs(y - ref) / _tol.complex_tol(ref)).max() <= 1.0
     dref = orc.powtodB(pref.copy())
     assert np.all(np.abs(p - dref) <= _tol.db_tol(dref, pref.max(axis=-1, keepdims=True)))
+
+
+@pytest.mark.parametrize('nfft', [1024, 2048, 4096, 8192, 16384])
+def test_few_frames_and_many_channels(cuda_device, nfft):
+    """edge shapes of the slot-per-frame kernels: a single frame, fewer frames than frame slots, more channels than
+    frames, a frame range that ends in the middle of a CTA's slots, band trim + dB -- against the oracle"""
+    for C, T, ovl in [(1, 1, 0.5), (5, 1, 0.0), (3, 2, 0.5), (2, 7, 0.75), (7, 3, 0.5)]:
+        nov = int(nfft * ovl)
+        hop = nfft - nov
+        n = (T - 1) * hop + nfft + (hop // 3 if T > 1 else 0)       # ragged tail shorter than a hop
+        x = synth(C * 31 + T, (C, n))
+        _, _, ref = orc.stft(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm='power')
+        assert ref.shape == (C, T, nfft)
+        y = iqw.stft(dev_of(x, cuda_device), fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1, norm='power',
+                     return_axis_arrays=False).cpu().numpy()
+        assert (np.abs(y - ref) / _tol.complex_tol(ref)).max() <= 1.0, (C, T, ovl)
+        kw = dict(fs=1e6, window='hann', resolution=1e6 / nfft, fractional_overlap=ovl, statistics=['max', 'min', 0.5],
+                  dB=True, axis=1, bandwidth=0.25e6)
+        got = iqw.persistence_spectrum(dev_of(x, cuda_device), **kw).cpu().numpy()
+        want = orc.persistence_spectrum(x, **kw)
+        _, _, p = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1)
+        assert got.shape == want.shape
+        _check_persistence(got, want, ['max', 'min', 0.5], x, nfft, True, p.max(axis=(1, 2))[:, None])
