@@ -313,6 +313,11 @@ int iqw_order_stats_finish_f32(const uint32_t* d_keys, int32_t n_sel, const int6
  * processed in chunks of that size. */
 int iqw_debug_set_stft_scratch_cap(size_t bytes);
 
+/* Tuning aid: columns of at least this many rows take the sampled one-read path of iqw_time_stats_f32
+ * (default 16384; 0 restores it); shorter ones the exact multi-pass pipeline.  Results are exact either way.
+ * Set it before iqw_time_stats_workspace_bytes: the workspace layout depends on the path. */
+int iqw_debug_set_sample_min_rows(int64_t rows);
+
 /* Tuning aid: which kernel-1 geometry serves nfft 1024 / 2048 / 4096.  0 = automatic (the two-pass
  * kernel, csrc/iqw_stft2p.cu: 32 / 64 values per thread, one shared-memory exchange per frame, frames
  * staged by bulk copies (TMA) when every frame start is 16-byte aligned), 1 = always the three-pass kernel

@@ -77,6 +77,7 @@ SIGNATURES = {
                                                   ctypes.POINTER(iqw_stat), _i32, _i32, _f32, _vp, _vp]),
     'iqw_debug_set_stft_scratch_cap': (ctypes.c_int, [_sz]),
     'iqw_debug_set_stft_variant': (ctypes.c_int, [ctypes.c_int]),
+    'iqw_debug_set_sample_min_rows': (ctypes.c_int, [_i64]),
     'iqw_debug_set_sample_margin': (ctypes.c_int, [ctypes.c_double, ctypes.c_int]),
     'iqw_debug_time_stats_counters': (ctypes.c_int, [_vp, _i64, ctypes.POINTER(ctypes.c_uint32)]),
     'iqw_profile_enable': (ctypes.c_int, [ctypes.c_int]),

@@ -1413,6 +1413,7 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
 // ranks the two SAMPLE ranks (margin-sigma away) whose keys bracket it.
 static std::atomic<double> g_margin_sigmas{5.0};   // iqw_debug_set_sample_margin; 5 sigma: ~1 % of config-3 calls refine one column
 static std::atomic<int> g_margin_extra{2};
+static std::atomic<long long> g_sample_min_rows{kSampleMinRows};   // iqw_debug_set_sample_min_rows
 
 struct LongPlan {
     long long splits, rows_per_split;
@@ -1653,6 +1654,11 @@ extern "C" int iqw_debug_set_sample_margin(double sigmas, int extra) {
     return IQW_OK;
 }
 
+extern "C" int iqw_debug_set_sample_min_rows(int64_t rows) {
+    g_sample_min_rows.store(rows < 1 ? kSampleMinRows : rows);
+    return IQW_OK;
+}
+
 extern "C" int iqw_debug_time_stats_counters(const void* d_workspace, int64_t n_cols, uint32_t* host_out16) {
     if (!d_workspace || !host_out16 || n_cols < 1) return fail(IQW_ERR_INVALID, "bad argument");
     Work w{};
@@ -1665,7 +1671,7 @@ extern "C" size_t iqw_time_stats_workspace_bytes(int64_t n_channels, int64_t n_r
                                                  int32_t n_stats) {
     (void)n_channels;
     if (n_cols <= 0) return 256;
-    if (n_rows < kSampleMinRows || n_stats < 1) return carve_work(nullptr, n_cols, 0, 0, nullptr);
+    if (n_rows < g_sample_min_rows.load() || n_stats < 1) return carve_work(nullptr, n_cols, 0, 0, nullptr);
     LongPlan lp{};
     plan_long_shape(n_rows, n_cols, &lp);
     const int groups = n_stats < kMaxGroups ? n_stats : kMaxGroups;
@@ -1695,7 +1701,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
 
     // long-column (sampled, one-read) path?
     LongPlan lp{};
-    const bool sampled = n_rows >= kSampleMinRows && rp.n_ranks > 0 &&
+    const bool sampled = n_rows >= g_sample_min_rows.load() && rp.n_ranks > 0 &&
                          build_long_plan(rp, n_rows, n_cols, n_stats, &lp);
     Work w{};
     const size_t need = sampled ? carve_work(d_workspace, n_cols, lp.splits, lp.bp.cap_sum, &w)

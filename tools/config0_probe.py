@@ -22,3 +22,15 @@ graphed = bench._timed(torch, lambda: g(), reps=10)
 with_copy = bench._timed(torch, lambda: g(x), reps=10)
 print('graph replay %.4f ms (%.1f GS/s, %.3f of the measured HBM peak at 24 B/sample); with the input copy %.4f ms; identical: %s'
       % (graphed, n / graphed / 1e6, 24 * n / graphed / 1e6 / bench.measured_peak()[0], with_copy, bool(torch.equal(g(), ref))))
+
+# the exact multi-pass pipeline instead of the sampled one-read path (the 123 MB matrix fits the L2)
+_lib.lib.iqw_debug_set_sample_min_rows(1 << 30)
+ex = bench._timed(torch, lambda: iqw.persistence_spectrum(x, **kw), reps=10)
+_lib.profile(True, fine=True)
+out2 = iqw.persistence_spectrum(x, **kw).clone()
+torch.cuda.synchronize()
+rep = _lib.profile_report(); _lib.profile(False)
+print('exact pipeline: plain call %.4f ms, identical %s; kernels: %s' % (ex, bool(torch.equal(out2, ref)), ', '.join(f'{k} {c}x {ms:.4f}' for k, (c, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]))))
+g2 = iqw.GraphedCall(iqw.persistence_spectrum, x, **kw)
+print('exact pipeline as a graph: %.4f ms' % bench._timed(torch, lambda: g2(), reps=10))
+_lib.lib.iqw_debug_set_sample_min_rows(0)
