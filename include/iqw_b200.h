@@ -189,6 +189,11 @@ int iqw_elementwise_f32(int32_t op, const float* d_in, float* d_out, int64_t n, 
                         void* stream);
 int iqw_elementwise_c64(int32_t op, const void* d_in, float* d_out, int64_t n, float eps, void* stream);
 
+/* (batch, rows, cols) complex64 -> (batch, cols, rows): brings a capture whose time axis is not the last one
+ * ((N, C) with axis = 0, util.py:400-442) to the (channels, time) layout of the kernels without a framework
+ * copy on the data path.  cols <= 2 097 120, batch <= 65535. */
+int iqw_transpose_c64(const void* d_in, int64_t batch, int64_t rows, int64_t cols, void* d_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Kernel 4: inverse STFT with overlap-add, optionally band-masked / zero-padded / filtered
  * (istft, ola_filter, oaresample).

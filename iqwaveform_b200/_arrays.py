@@ -69,12 +69,34 @@ def as_channels(x: torch.Tensor, axis: int) -> tuple[torch.Tensor, tuple, tuple]
         raise ValueError(f'axis {axis} exceeds the number of dimensions')
     lead, trail = tuple(x.shape[:axis]), tuple(x.shape[axis + 1:])
     if trail:
+        t = _transpose_time_last(x, axis, lead, trail)
+        if t is not None:
+            return t, lead, trail
         x = x.movedim(axis, -1)
     n = x.shape[-1]
     x2 = x.reshape(-1, n)
     if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < n):
         x2 = x2.contiguous()
     return x2, lead, trail
+
+
+def _transpose_time_last(x: torch.Tensor, axis: int, lead: tuple, trail: tuple):
+    """(lead..., N, trail...) contiguous complex64 on the device -> (prod(lead) * prod(trail), N) through the
+    library's tiled transpose (csrc/iqw_elementwise.cu); None when the tensor does not qualify (the caller then
+    lets torch make the copy)"""
+    import ctypes
+    import math
+    from . import _lib
+    if not (x.is_cuda and x.dtype == torch.complex64 and x.is_contiguous()):
+        return None
+    n = x.shape[axis]
+    batch, cols = math.prod(lead), math.prod(trail)
+    if batch > 65535 or cols > 65535 * 32 or n == 0 or cols == 0 or batch == 0:
+        return None
+    out = torch.empty((batch * cols, n), dtype=torch.complex64, device=x.device)
+    _lib.check(_lib.lib.iqw_transpose_c64(ctypes.c_void_p(x.data_ptr()), batch, n, cols, ctypes.c_void_p(out.data_ptr()),
+                                          ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out
 
 
 def restore_layout(y: torch.Tensor, lead: tuple, trail: tuple, new_axes: int) -> torch.Tensor:

@@ -64,6 +64,7 @@ SIGNATURES = {
     'iqw_envtopow_transposed_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     'iqw_elementwise_f32': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i32, _f32, _vp]),
     'iqw_elementwise_c64': (ctypes.c_int, [_i32, _vp, _vp, _i64, _f32, _vp]),
+    'iqw_transpose_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     'iqw_istft_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _i64, _vp]),
     'iqw_ifft_c64': (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     'iqw_ola_filter_c64': (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),

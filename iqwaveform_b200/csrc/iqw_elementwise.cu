@@ -140,3 +140,48 @@ extern "C" int iqw_elementwise_c64(int32_t op, const void* d_in, float* d_out, i
     IQW_CUDA_OK(cudaGetLastError());
     return IQW_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// layout: captures whose time axis is not the last one -- (N, C) with axis = 0, the layout the
+// reference's noverlap = 0 path accepts (util.py:400-442 to_blocks) -- are brought to the (C, N)
+// channel layout of the kernels by a tiled transpose through shared memory (8-byte elements,
+// 32 x 32 tiles, both sides coalesced) instead of a framework copy kernel on the data path.
+//   in  (batch, rows, cols) complex64 contiguous  ->  out (batch, cols, rows)
+// Bound: HBM, 16 B per sample.
+// ---------------------------------------------------------------------------------------------
+namespace iqw {
+__global__ void __launch_bounds__(256) transpose_c64_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                             long long rows, long long cols) {
+    __shared__ float2 tile[32][33];
+    const long long b = blockIdx.z;
+    const float2* src = in + b * rows * cols;
+    float2* dst = out + b * rows * cols;
+    const long long r0 = (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;   // the long axis on grid.x
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long long r = r0 + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[i][tx] = __ldcs(src + r * cols + c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long long c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) __stcs(dst + c * rows + r, tile[tx][i]);
+    }
+}
+}  // namespace iqw
+
+extern "C" int iqw_transpose_c64(const void* d_in, int64_t batch, int64_t rows, int64_t cols, void* d_out, void* stream) {
+    iqw::DeviceGuard _dev_guard(d_in);
+    if (!d_in || !d_out) return fail(IQW_ERR_INVALID, "null pointer argument");
+    if (batch < 0 || rows < 0 || cols < 0) return fail(IQW_ERR_INVALID, "negative size");
+    if (batch == 0 || rows == 0 || cols == 0) return IQW_OK;
+    const long long gx = (rows + 31) / 32, gy = (cols + 31) / 32;
+    if (gx > 0x7FFFFFFFll || gy > 65535 || batch > 65535)
+        return fail(IQW_ERR_UNSUPPORTED, "iqw_transpose_c64: more than 65535 column tiles or batches");
+    transpose_c64_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(d_in), static_cast<float2*>(d_out), rows, cols);
+    IQW_CUDA_OK(cudaGetLastError());
+    return IQW_OK;
+}

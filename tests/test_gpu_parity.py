@@ -610,3 +610,23 @@ def test_few_frames_and_many_channels(cuda_device, nfft):
         _, _, p = orc.spectrogram(x, fs=1e6, window='hann', nperseg=nfft, noverlap=nov, axis=1)
         assert got.shape == want.shape
         _check_persistence(got, want, ['max', 'min', 0.5], x, nfft, True, p.max(axis=(1, 2))[:, None])
+
+
+def test_time_axis_first_layouts_use_the_library_transpose(cuda_device):
+    """(N, C) axis=0 and (B, N, C) axis=1 captures: the tiled transpose kernel brings them to (channels, time);
+    same results as the (C, N) axis=1 call"""
+    from iqwaveform_b200 import _arrays
+    x = synth(4, (3, 40000))
+    xd = dev_of(x, cuda_device)
+    t2, lead, trail = _arrays.as_channels(xd.T.contiguous(), 0)
+    assert torch.equal(t2, xd) and lead == () and trail == (3,)
+    x3 = torch.stack([xd.T.contiguous(), 2 * xd.T.contiguous()])          # (2, N, 3)
+    t3, lead, trail = _arrays.as_channels(x3, 1)
+    assert t3.shape == (6, 40000) and torch.equal(t3[:3], xd) and torch.equal(t3[3:], 2 * xd)
+    want = iqw.iq_to_bin_power(xd, 1e-6, 1e-4, kind='mean', axis=1)
+    got = iqw.iq_to_bin_power(xd.T.contiguous(), 1e-6, 1e-4, kind='mean', axis=0)
+    assert torch.equal(got, want.T)
+    _, _, w0 = orc.stft(x, fs=1.0, window='hann', nperseg=256, noverlap=0, axis=1, norm='power')
+    y = iqw.stft(xd.T.contiguous(), fs=1.0, window='hann', nperseg=256, noverlap=0, axis=0, norm='power',
+                 return_axis_arrays=False)
+    np.testing.assert_allclose(y.cpu().numpy(), np.moveaxis(w0, 0, -1), atol=2e-7 * np.abs(w0).max())
