@@ -308,6 +308,37 @@ static int launch_stft_reduce(StftArgs a, const ReducePlan& st, float* out, void
     return IQW_OK;
 }
 
+// nfft 1024 / 2048 / 4096 with at most two of {max, min, sum}: the warp-specialised two-pass kernel (iqw_stft2p.cu)
+static int launch_stft_reduce_two_pass(StftArgs a, int log2n, const ReducePlan& st, float* out, void* ws, size_t ws_bytes,
+                                       cudaStream_t stream, bool* done) {
+    *done = false;
+    if (stft_variant() == 1 || log2n < 10 || log2n > 12) return IQW_OK;
+    int flags = 0;
+    for (int t = 0; t < st.n_stats; ++t)
+        flags |= st.kind[t] == IQW_STAT_MAX ? 1 : st.kind[t] == IQW_STAT_MIN ? 2 : 4;
+    int sms = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    const long long N = 1ll << log2n;
+    const size_t need = (size_t)sms * N * (2 * sizeof(float) + sizeof(double));
+    if (!ws || ws_bytes < need) return fail(IQW_ERR_WORKSPACE, "stft reduce workspace %zu bytes < required %zu", ws_bytes, need);
+    a.n_channels = 1;
+    a.part_sum = static_cast<double*>(ws);
+    a.part_max = reinterpret_cast<float*>(a.part_sum + (size_t)sms * N);
+    a.part_min = a.part_max + (size_t)sms * N;
+    long long n_parts = 0;
+    const int rc = launch_stft_two_pass_reduce(a, log2n, flags, &n_parts, stream);
+    if (rc == IQW_ERR_UNSUPPORTED) return IQW_OK;
+    if (rc) return rc;
+    const int nb = a.bin_hi - a.bin_lo;
+    const int convert = a.reduce_dB;
+    { IQW_PROFILE_FINE("stft_reduce_combine", stream);
+      stft_reduce_combine_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(a.part_max, a.part_min, a.part_sum, (int)n_parts, (int)N,
+                                                                       a.bin_lo, a.bin_hi, a.n_frames, st, convert, a.eps, out); }
+    IQW_CUDA_OK(cudaGetLastError());
+    *done = true;
+    return IQW_OK;
+}
+
 }  // namespace iqw
 
 using namespace iqw;
@@ -359,6 +390,9 @@ extern "C" int iqw_stft_reduce_c64(const void* d_x, int64_t n_channels, int64_t 
         for (int t = 0; t < n_stats; ++t) a.reduce_flags |= stats[t].kind == IQW_STAT_MEAN ? 2 : 1;
         if (int rc = get_twiddles(log2n, s, &a.twiddle)) return rc;
         float* out = d_out + c * (int64_t)n_stats * nb;
+        bool done = false;
+        if (int rc2 = launch_stft_reduce_two_pass(a, log2n, st, out, d_workspace, workspace_bytes, s, &done)) return rc2;
+        if (done) continue;
         int rc = IQW_ERR_UNSUPPORTED;
         switch (log2n) {
             case 4: rc = launch_stft_reduce<4>(a, st, out, d_workspace, workspace_bytes, s); break;

@@ -86,6 +86,10 @@ int get_twiddles(int log2n, cudaStream_t stream, const float2** out);
 bool stft_two_pass_wanted(int log2n);
 int launch_stft_two_pass(const StftArgs& a, int log2n, int mode, cudaStream_t stream);
 
+// reducible statistics fused into the two-pass kernel (warp-specialised; iqw_stft2p.cu).  flags: bit 0 max, bit 1 min,
+// bit 2 sum; IQW_ERR_UNSUPPORTED for all three at once.  Leaves *n_parts partial rows in a.part_max / min / sum.
+int launch_stft_two_pass_reduce(const StftArgs& a, int log2n, int flags, long long* n_parts, cudaStream_t stream);
+
 // nfft 8192 .. 65536 in one pass: frame in (distributed) shared memory, cluster of 1 / 1 / 2 / 4 CTAs (iqw_stft3p.cu)
 bool stft_three_pass_cluster_ok(const StftArgs& a, int log2n);
 size_t stft_three_pass_scratch_bytes(int log2n, long long n_channels, long long n_frames);

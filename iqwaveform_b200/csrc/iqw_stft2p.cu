@@ -323,6 +323,293 @@ static int launch2p(const StftArgs& a, int mode, cudaStream_t s) {
     return fail(IQW_ERR_INVALID, "unknown stft mode %d", mode);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Reducible statistics fused into the two-pass kernel (iqw_stft_reduce_c64 at nfft 1024 / 2048 / 4096):
+// WARP SPECIALISATION.  A thread of the transform holds 64 values and has no registers left for 64 + 64
+// running statistics, so the CTA carries a second role: PS producer slots run the two-pass transform
+// exactly as stft2p_kernel does and, instead of storing |X|^2 to HBM, hand each frame to a consumer group
+// through a per-slot power tile in shared memory (N floats) guarded by a full / empty mbarrier pair; the CT
+// consumer threads own the bins k = ct + CT*i of EVERY frame of the CTA and keep their running max / min / sum
+// in registers (two of the three: 128 registers).  Sums are flushed every 64 frames into a float64 partial row
+// in global memory (two-level summation); max / min leave at the end.  Four consumer warps (a thread owns 32 / 16 / 8
+// bins at nfft 4096 / 2048 / 1024) keep up with the eight producer warps; all three statistics fit their registers and
+// the logarithms of a mean of dB values run there, beside the FMA-bound transform of the producers.  stft_reduce_combine_kernel
+// (iqw_stft.cu) then combines the per-CTA rows.  Nothing is written per frame: 8 B/sample of HBM traffic.
+// ---------------------------------------------------------------------------------------------------
+template <int LOG2N>
+struct P2RCfg {
+    using B = P2Cfg<LOG2N, true>;
+    static constexpr int PS = LOG2N == 12 ? 4 : 8;                 // producer slots (8 producer warps)
+    static constexpr int CT = 128;                                 // consumer threads: four warps keep up with eight producer warps
+    static constexpr int BPT = B::N / CT;                          // bins per consumer thread: 32 / 16 / 8
+    static constexpr int PTHREADS = PS * B::TPF;                   // 256
+    static constexpr int THREADS = PTHREADS + CT;                  // 384: 12 warps, 168 registers per thread
+    static constexpr size_t SMEM = sizeof(float2) * ((size_t)B::TW + (size_t)PS * B::BUF) + sizeof(float) * (size_t)PS * B::N;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// FLAGS: bit 0 = max, bit 1 = min, bit 2 = sum (of dB values when a.reduce_dB)
+template <int LOG2N, int FLAGS, bool STAGED>
+__global__ void __launch_bounds__(P2RCfg<LOG2N>::THREADS, 1)
+stft2p_reduce_kernel(const StftArgs a) {
+    using C = P2Cfg<LOG2N, true>;
+    using R = P2RCfg<LOG2N>;
+    constexpr int RA = C::RA, RB = C::RB, E = C::E, TPF = C::TPF, NB = C::NB, ROW = C::ROW, N = C::N;
+    constexpr int PS = R::PS, CT = R::CT, BPT = R::BPT;
+    constexpr bool WMAX = (FLAGS & 1) != 0, WMIN = (FLAGS & 2) != 0, WSUM = (FLAGS & 4) != 0;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    float* ptiles = reinterpret_cast<float*>(tw + C::TW + (size_t)PS * C::BUF);
+    __shared__ __align__(8) uint64_t in_bar[PS], full_bar[PS], empty_bar[PS];
+    for (int i = threadIdx.x; i < C::TW; i += R::THREADS) tw[i] = a.twiddle[i];
+    if (threadIdx.x < PS) {
+        mbar_init(&in_bar[threadIdx.x], 1);
+        mbar_init(&full_bar[threadIdx.x], TPF);
+        mbar_init(&empty_bar[threadIdx.x], CT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+    __syncthreads();
+
+    // frame range of every producer slot (the consumers need all of them)
+    const long long total = a.n_frames;                                   // one channel per launch
+    const long long n_slots = (long long)gridDim.x * PS;
+    const long long per = (total + n_slots - 1) / n_slots;
+    auto slot_begin = [&](int sl) { return ((long long)blockIdx.x * PS + sl) * per; };
+    auto slot_end = [&](int sl) { const long long b = slot_begin(sl) + per; return b < total ? b : total; };
+
+    if (threadIdx.x >= R::PTHREADS) {
+        // ------------------------------ consumer ------------------------------
+        const int ct = threadIdx.x - R::PTHREADS;
+        float mx[WMAX ? BPT : 1], mn[WMIN ? BPT : 1], sm[WSUM ? BPT : 1];
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            if (WMAX) mx[i] = -INFINITY;
+            if (WMIN) mn[i] = INFINITY;
+            if (WSUM) sm[i] = 0.f;
+        }
+        const long long part = (long long)blockIdx.x * N;
+        if (WSUM) {
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) a.part_sum[part + ct + CT * i] = 0.0;
+        }
+        long long cnt[PS], most = 0;
+#pragma unroll
+        for (int sl = 0; sl < PS; ++sl) {
+            cnt[sl] = slot_end(sl) - slot_begin(sl);
+            if (cnt[sl] < 0) cnt[sl] = 0;
+            most = cnt[sl] > most ? cnt[sl] : most;
+        }
+        int since = 0;
+        for (long long it = 0; it < most; ++it) {
+#pragma unroll
+            for (int sl = 0; sl < PS; ++sl) {
+                if (it >= cnt[sl]) continue;
+                mbar_wait(&full_bar[sl], (uint32_t)(it & 1));
+                const float* pt = ptiles + sl * N + ct;
+                // the tile is taken 16 values at a time (reading all 32 first and handing the tile back earlier was
+                // measured: more live registers, 5.4 against 5.1 ms at nfft 4096)
+                constexpr int QB = BPT < 16 ? BPT : 16;
+#pragma unroll
+                for (int h = 0; h < BPT; h += QB) {
+                    float p[QB];
+#pragma unroll
+                    for (int j = 0; j < QB; ++j) p[j] = pt[CT * (h + j)];
+                    if (h + QB >= BPT) mbar_arrive(&empty_bar[sl]);       // last read issued: the tile may be overwritten
+#pragma unroll
+                    for (int j = 0; j < QB; ++j) {
+                        if (WMAX) mx[h + j] = fmaxf(mx[h + j], p[j]);
+                        if (WMIN) mn[h + j] = fminf(mn[h + j], p[j]);
+                    }
+                    if (WSUM) {
+                        if (a.reduce_dB) {
+                            // branch-free lg2 of the quarter; zero / denormal / inf / nan arguments are rare and take
+                            // log10f behind one branch
+                            bool all_ok = true;
+#pragma unroll
+                            for (int j = 0; j < QB; ++j) {
+                                p[j] = fabsf(p[j]) + a.eps;
+                                all_ok &= dB_fast_ok(p[j]);
+                            }
+                            if (all_ok) {
+#pragma unroll
+                                for (int j = 0; j < QB; ++j) { bool ok; sm[h + j] += power_to_dB_fast(p[j], ok); }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < QB; ++j) {
+                                    bool ok;
+                                    const float d = power_to_dB_fast(p[j], ok);
+                                    sm[h + j] += ok ? d : power_to_dB_slow(p[j]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < QB; ++j) sm[h + j] += p[j];
+                        }
+                    }
+                }
+                if (WSUM) {
+                    if (++since == 64) {                                  // two-level summation
+                        since = 0;
+#pragma unroll
+                        for (int i = 0; i < BPT; ++i) { a.part_sum[part + ct + CT * i] += (double)sm[i]; sm[i] = 0.f; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const long long k = part + ct + CT * i;
+            a.part_max[k] = WMAX ? mx[i] : -INFINITY;
+            a.part_min[k] = WMIN ? mn[i] : INFINITY;
+            if (WSUM) a.part_sum[k] += (double)sm[i];
+            else a.part_sum[k] = 0.0;
+        }
+        return;
+    }
+
+    // ------------------------------ producers: the two-pass transform of stft2p_kernel ------------------------------
+    const int slot = threadIdx.x / TPF;
+    const int ltid = threadIdx.x % TPF;
+    float2* buf = tw + C::TW + (size_t)slot * C::BUF;
+    float* ptile = ptiles + slot * N;
+    constexpr uint32_t kFrameBytes = (uint32_t)(N * sizeof(float2));
+    auto slot_sync = [&]() {
+        if constexpr (TPF == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(TPF) : "memory");
+    };
+    long long frame = slot_begin(slot);
+    const long long f_end = slot_end(slot);
+    if (frame >= f_end) return;
+    const float* wp = a.window + ltid;
+    uint32_t parity = 0;
+    if constexpr (STAGED) {
+        if (ltid == 0) {
+            mbar_expect_tx(&in_bar[slot], kFrameBytes);
+            bulk_load(buf, a.x + frame * a.hop, kFrameBytes, &in_bar[slot]);
+        }
+    }
+    for (long long it = 0; frame < f_end; ++frame, ++it) {
+        float2 v[E];
+        {
+            float w[RA];
+#pragma unroll
+            for (int r = 0; r < RA; ++r) w[r] = __ldg(wp + r * RB);
+            if constexpr (STAGED) {
+                mbar_wait(&in_bar[slot], parity);
+                parity ^= 1;
+#pragma unroll
+                for (int r = 0; r < RA; ++r) v[r] = buf[ltid + r * RB];
+            } else {
+                const float2* src = a.x + frame * a.hop + ltid;
+#pragma unroll
+                for (int r = 0; r < RA; ++r) v[r] = ldg_stream(src + r * RB);
+            }
+            bfly_big_scaled<RA>(v, w);
+        }
+        slot_sync();
+        {
+            float4* row = reinterpret_cast<float4*>(buf + ltid * ROW);
+#pragma unroll
+            for (int k = 0; k < RA; k += 2) row[k / 2] = make_float4(v[k].x, v[k].y, v[k + 1].x, v[k + 1].y);
+        }
+        slot_sync();
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int jB = ltid + q * TPF;
+            float2* u = v + q * RB;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) u[r] = buf[r * ROW + jB];
+        }
+        if constexpr (STAGED) {
+            slot_sync();
+            if (ltid == 0 && frame + 1 < f_end) {
+                fence_proxy_async();
+                mbar_expect_tx(&in_bar[slot], kFrameBytes);
+                bulk_load(buf, a.x + (frame + 1) * a.hop, kFrameBytes, &in_bar[slot]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int jB = ltid + q * TPF;
+            float2* u = v + q * RB;
+            float2 A[C::NA8], B[8];
+            A[0] = make_float2(1.f, 0.f);
+            B[0] = make_float2(1.f, 0.f);
+#pragma unroll
+            for (int k = 1; k < C::NA8; ++k) A[k] = tw[(k - 1) * RA + jB];
+#pragma unroll
+            for (int b = 1; b < 8; ++b) B[b] = tw[(C::NA8 - 1 + b - 1) * RA + jB];
+            bfly_big_twiddled<RB>(u, A, B);
+        }
+        // the frame's power
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i].x = v[i].x * v[i].x + v[i].y * v[i].y;
+        // hand it to the consumers (wait until they have taken the previous frame of this slot)
+        if (it > 0) mbar_wait(&empty_bar[slot], (uint32_t)((it - 1) & 1));
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int r = 0; r < RB; ++r) ptile[ltid + q * TPF + r * RA] = v[q * RB + r].x;
+        mbar_arrive(&full_bar[slot]);
+    }
+}
+
+template <int LOG2N, int FLAGS>
+static int launch2p_reduce_flags(StftArgs a, long long* n_parts, cudaStream_t stream) {
+    using R = P2RCfg<LOG2N>;
+    const bool staged = g_stft_variant.load() != 2 && frames_16B_aligned(a);
+    if (int rc = get_twiddles2p<LOG2N>(stream, &a.twiddle)) return rc;
+    int sms = 0;
+    if (int rc = device_sm_count(&sms)) return rc;
+    long long grid = sms;
+    const long long need = (a.n_frames + R::PS - 1) / R::PS;
+    if (grid > need) grid = need;
+    *n_parts = grid;
+    if (staged) {
+        auto kern = stft2p_reduce_kernel<LOG2N, FLAGS, true>;
+        IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::SMEM));
+        IQW_PROFILE("stft_reduce_kernel", stream);
+        kern<<<(unsigned)grid, R::THREADS, R::SMEM, stream>>>(a);
+    } else {
+        auto kern = stft2p_reduce_kernel<LOG2N, FLAGS, false>;
+        IQW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::SMEM));
+        IQW_PROFILE("stft_reduce_kernel", stream);
+        kern<<<(unsigned)grid, R::THREADS, R::SMEM, stream>>>(a);
+    }
+    IQW_CUDA_OK(cudaGetLastError());
+    return IQW_OK;
+}
+
+// flags: bit 0 max, bit 1 min, bit 2 sum; returns IQW_ERR_UNSUPPORTED when all three are wanted (the caller then
+// takes the three-pass kernel, whose 16 values per thread leave room for all of them)
+int launch_stft_two_pass_reduce(const StftArgs& a, int log2n, int flags, long long* n_parts, cudaStream_t stream) {
+#define IQW_R2(L, F) return launch2p_reduce_flags<L, F>(a, n_parts, stream)
+#define IQW_R2F(L)                                    \
+    switch (flags) {                                  \
+        case 1: IQW_R2(L, 1);                         \
+        case 2: IQW_R2(L, 2);                         \
+        case 3: IQW_R2(L, 3);                         \
+        case 4: IQW_R2(L, 4);                         \
+        case 5: IQW_R2(L, 5);                         \
+        case 6: IQW_R2(L, 6);                         \
+        case 7: IQW_R2(L, 7);                         \
+        default: return IQW_ERR_UNSUPPORTED;          \
+    }
+    switch (log2n) {
+        case 10: IQW_R2F(10)
+        case 11: IQW_R2F(11)
+        case 12: IQW_R2F(12)
+    }
+#undef IQW_R2F
+#undef IQW_R2
+    return IQW_ERR_UNSUPPORTED;
+}
+
 int stft_variant() { return g_stft_variant.load(); }
 
 bool stft_two_pass_wanted(int log2n) {
