@@ -11,7 +11,8 @@ import os
 import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to the same runtime)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libiqw_b200.so')
+# IQW_B200_LIB: another build of the same library (kernel experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get('IQW_B200_LIB') or os.path.join(_HERE, 'libiqw_b200.so')
 
 ABI_VERSION = 8
 

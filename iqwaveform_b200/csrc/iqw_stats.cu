@@ -136,7 +136,8 @@ struct Work {
     uint32_t* bk_lo;      // [cols][kMaxGroups] bracket bounds (empty slot: lo > hi)
     uint32_t* bk_hi;
     uint32_t* t_below;    // [cols][kMaxGroups] keys below each bracket, all rows
-    uint32_t* t_cnt;      // [cols][kMaxGroups] keys inside each bracket, all rows
+    uint32_t* t_cnt;      // [cols][kMaxGroups] keys in the bracket's region (bracket + the gap after it), from scan_brackets
+    uint32_t* t_gap_hi;   // [cols][kMaxGroups] last key of that gap
     uint32_t* t_ovf;      // [cols] != 0: some candidate list of the column overflowed
     uint32_t* s_cnt;      // [splits][cols] keys in each candidate list
     uint32_t* lists;      // [splits][cols][cap_sum] candidate keys (of all brackets, unordered)
@@ -189,6 +190,7 @@ static size_t carve_work(void* base, int64_t cols, int64_t splits, int64_t cap_s
     if (splits > 0) {
         t.bk_lo = (uint32_t*)take(4 * c * g);
         t.bk_hi = (uint32_t*)take(4 * c * g);
+        t.t_gap_hi = (uint32_t*)take(4 * c * g);
         t.s_cnt = (uint32_t*)take(4 * (size_t)splits * c);
         t.lists = (uint32_t*)take(4 * (size_t)splits * c * (size_t)cap_sum);
     }
@@ -479,54 +481,61 @@ __global__ void scan_refine_kernel(long long cols, RankPlan rp, Work w) {
     iv_store(L, w, col);
 }
 
-// after the bracket pass (long-column path): regions in key order are gap, bracket 0, gap,
-// bracket 1, ..., gap with exact counts; locate every target rank in its region.  A rank inside a
-// bracket whose lists did not overflow becomes a SELECT interval (its keys are in the candidate
-// lists); anything else becomes a generic interval that the exact pipeline refines.
+// after the bracket pass (long-column path): the number of keys below every bracket is known, the number
+// INSIDE is not (select_kernel counts it from the lists).  Regions in key order: the gap below the first
+// bracket, then per bracket the bracket TOGETHER WITH the gap that follows it.  Every target rank is located
+// in its region.  A rank in the region of a bracket whose lists did not overflow becomes a SELECT interval
+// (select_kernel moves it on to the gap if it lies beyond the bracket's keys); anything else becomes a
+// generic interval that the exact pipeline refines.
 __global__ void scan_brackets_kernel(long long cols, long long rows, RankPlan rp, int n_groups,
                                      Work w) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= cols) return;
     IvList L;
     L.n = 0;
-    uint32_t cum = 0, i = 0;
+    uint32_t i = 0;
     const uint32_t nrk = (uint32_t)rp.n_ranks;
-    unsigned long long gap_start = 0ull;
     const uint32_t ovf = w.t_ovf[col];
+    bool first_live = true;
     for (int g = 0; g < n_groups && i < nrk; ++g) {
         const uint32_t lo = w.bk_lo[col * kMaxGroups + g], hi = w.bk_hi[col * kMaxGroups + g];
         if (lo > hi) continue;                                     // slot merged into an earlier one
-        const uint32_t below = w.t_below[col * kMaxGroups + g], cnt = w.t_cnt[col * kMaxGroups + g];
-        if (rp.rank[i] < below) {                                  // a bracket missed: rank is in the gap
+        const uint32_t below = w.t_below[col * kMaxGroups + g];
+        // the region ends where the next live bracket starts
+        unsigned long long next_lo = 0x100000000ull;
+        uint32_t next_below = (uint32_t)rows;
+        for (int h = g + 1; h < n_groups; ++h) {
+            const uint32_t l2 = w.bk_lo[col * kMaxGroups + h];
+            if (l2 <= w.bk_hi[col * kMaxGroups + h]) { next_lo = l2; next_below = w.t_below[col * kMaxGroups + h]; break; }
+        }
+        if (first_live && rp.rank[i] < below) {                    // ranks below the first bracket
             const uint32_t first = i;
             while (i < nrk && rp.rank[i] < below) ++i;
             atomicAdd(w.pending + 2, i - first);
-            iv_append(L, w, col, (uint32_t)gap_start, (unsigned long long)lo - gap_start, cum,
-                      below - cum, first, i - first, false, 0u);
+            iv_append(L, w, col, 0u, (unsigned long long)lo, 0u, below, first, i - first, false, 0u);
         }
-        cum = below;
-        if (i < nrk && rp.rank[i] < cum + cnt) {
+        first_live = false;
+        if (i < nrk && rp.rank[i] < next_below) {
             const uint32_t first = i;
-            while (i < nrk && rp.rank[i] < cum + cnt) ++i;
-            if (ovf || lo == hi) {
-                if (lo != hi) atomicAdd(w.pending + 3, 1u);
-                iv_append(L, w, col, lo, (unsigned long long)hi - lo + 1ull, cum, cnt, first,
-                          i - first, lo == hi, lo);
+            while (i < nrk && rp.rank[i] < next_below) ++i;
+            const uint32_t region = next_below - below;
+            if (ovf) {
+                atomicAdd(w.pending + 3, 1u);
+                iv_append(L, w, col, lo, next_lo - lo, below, region, first, i - first, false, 0u);
             } else {
                 const uint32_t v = L.n++;
-                L.klo[v] = lo; L.khi[v] = hi; L.below[v] = cum; L.cnt[v] = cnt;
+                L.klo[v] = lo; L.khi[v] = hi; L.below[v] = below; L.cnt[v] = region;
                 L.first[v] = first; L.nr[v] = i - first;
                 L.shift[v] = (uint32_t)g; L.status[v] = IV_SELECT;
+                w.t_cnt[col * kMaxGroups + g] = region;
+                w.t_gap_hi[col * kMaxGroups + g] = (uint32_t)(next_lo - 1ull);
                 atomicAdd(w.pending + 7, 1u);
             }
         }
-        cum += cnt;
-        gap_start = (unsigned long long)hi + 1ull;
     }
-    if (i < nrk) {                                                 // ranks above the last bracket
+    if (i < nrk) {                                                 // no live bracket at all
         atomicAdd(w.pending + 2, nrk - i);
-        iv_append(L, w, col, (uint32_t)gap_start, 0x100000000ull - gap_start, cum,
-                  (uint32_t)rows - cum, i, nrk - i, false, 0u);
+        iv_append(L, w, col, 0u, 0x100000000ull, 0u, (uint32_t)rows, i, nrk - i, false, 0u);
     }
     iv_store(L, w, col);
 }
@@ -770,12 +779,117 @@ __device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, l
     for (int g = 0; g < M; ++g) {
         const bool live = RAW ? (int32_t)lo[g] <= (int32_t)hi[g] : lo[g] <= hi[g];
         if (g < bp.n_groups && live) {
-            const uint32_t ge = (uint32_t)n_ge[g], in = (uint32_t)n_in[g];
+            const uint32_t ge = (uint32_t)n_ge[g];
             if (n - ge) atomicAdd(w.t_below + col * kMaxGroups + g, n - ge);
-            if (in) atomicAdd(w.t_cnt + col * kMaxGroups + g, in);
         }
     }
     const uint32_t n_list = n_lines * kLine + rem_mine;
+    w.s_cnt[(long long)blockIdx.y * cols + col] = min(n_list, cap);
+    if (n_list > cap) atomicOr(w.t_ovf + col, 1u);
+    named.flush(w, col);
+}
+
+// RAW mode for M <= 4 brackets: difference form of the per-key body (bracket_visit_diff, 3M + 4 instructions)
+// and a 32-key staging RING per thread which its OWNER drains, 16 keys (64 bytes, two full sectors) at a time
+// with four 128-bit loads and stores: no warp-wide step, nothing is moved inside the buffer.  The keys
+// INSIDE each bracket are not counted here: select_kernel counts them when it histograms the lists.
+constexpr int kRing = 32;                       // keys per thread: one chunk being filled, one being drained
+constexpr int kChunk = 16;                      // keys per drain
+#ifndef IQW_BP_PREFETCH
+#define IQW_BP_PREFETCH 48
+#endif
+constexpr int kPrefetchRows = IQW_BP_PREFETCH;  // L2 prefetch distance of the bracket pass, in rows (multiple of kUnroll; 0: off)
+
+template <int M, int NAMED>
+__device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__ p, long long cols, long long col,
+                                                       bool live_col, long long i0, long long i1, float eps,
+                                                       const BracketPlan& bp, const Work& w, uint32_t* stage) {
+    uint32_t lo[M], wd[M];       // raw-bit low bound (open low end: 0) and width hi - lo + 1 (empty slot: 0)
+    uint32_t nlt[M];             // keys below lo[g]
+#pragma unroll
+    for (int g = 0; g < M; ++g) {
+        const uint32_t klo = live_col ? w.bk_lo[col * kMaxGroups + g] : 0xFFFFFFFFu;
+        const uint32_t khi = live_col ? w.bk_hi[col * kMaxGroups + g] : 0u;
+        lo[g] = 0u; wd[g] = 0u; nlt[g] = 0u;
+        if (klo <= khi) {
+            // RAW mode: klo is 0 (open) or the key of a float > +0, khi the key of a float >= +0 or 0xFFFFFFFF
+            lo[g] = klo < 0x80000000u ? 0u : klo ^ 0x80000000u;
+            wd[g] = (khi ^ 0x80000000u) - lo[g] + 1u;
+        }
+    }
+    const uint32_t cap = bp.cap_sum;                    // multiple of kLine, hence of kChunk
+    uint32_t* my_stage = stage + threadIdx.x * kRing;
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(my_stage);    // 128-byte aligned
+    uint32_t p4 = 0;                                    // bytes appended so far (4 per key)
+    uint32_t n_chunks = 0;                              // chunks taken out of the ring so far
+    // this thread's list in this row split (a thread past the last column never appends: its brackets are empty)
+    uint32_t* my_list = w.lists + ((long long)blockIdx.y * cols + col) * (long long)cap;
+    Named<(NAMED & 1) != 0, (NAMED & 2) != 0, (NAMED & 4) != 0> named;
+
+    auto drain = [&](uint32_t at_least) {
+        if ((p4 >> 2) - n_chunks * kChunk >= at_least) {
+            const uint4* q = reinterpret_cast<const uint4*>(my_stage + ((n_chunks & 1u) << 4));
+            const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+            if ((n_chunks + 1u) * kChunk <= cap) {      // a full list keeps counting; the column is flagged below
+                uint4* d = reinterpret_cast<uint4*>(my_list + n_chunks * kChunk);
+                d[0] = q0; d[1] = q1; d[2] = q2; d[3] = q3;
+            }
+            ++n_chunks;
+        }
+    };
+    auto visit = [&](float f) {
+        if (NAMED) named.add(f, float_to_key(f), eps);
+        bracket_visit_diff(__float_as_uint(f), nlt, p4, lo, wd, stage_addr);
+    };
+    const float* src = p + i0 * cols + col;
+    long long i = i0;
+    float fa[kUnroll], fb[kUnroll];
+    auto load_block = [&](float (&f)[kUnroll]) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u, src += cols) f[u] = __ldcs(src);
+    };
+    auto visit_block = [&](float (&f)[kUnroll]) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) visit(f[u]);
+        drain(kChunk);          // at most kChunk - 1 + kUnroll < kRing keys are ever in the ring
+    };
+    // One thread per CTA asks the L2 for the CTA's 512-byte row segments kPrefetchRows ahead (bulk prefetch, one
+    // instruction per row).
+    const bool pf_on = threadIdx.x == 0 && (cols & 3) == 0 && (long long)(blockIdx.x + 1) * kBX <= cols;
+    auto prefetch_block = [&](long long row) {     // rows row .. row + kUnroll - 1 of this CTA's column tile
+        if (kPrefetchRows > 0 && pf_on && row + kUnroll <= i1) {
+            const float* q = p + row * cols + (long long)blockIdx.x * kBX;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u, q += cols)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(q), "r"((uint32_t)(kBX * sizeof(float))) : "memory");
+        }
+    };
+    for (int b = 2; b < kPrefetchRows / kUnroll; ++b) prefetch_block(i0 + (long long)b * kUnroll);
+    if (i + kUnroll <= i1) load_block(fa);
+#pragma unroll 1
+    while (i + kUnroll <= i1) {
+        if (i + 2 * kUnroll <= i1) load_block(fb);
+        prefetch_block(i + kPrefetchRows);
+        visit_block(fa);
+        i += kUnroll;
+        if (i + kUnroll > i1) break;
+        if (i + 2 * kUnroll <= i1) load_block(fa);
+        prefetch_block(i + kPrefetchRows);
+        visit_block(fb);
+        i += kUnroll;
+    }
+#pragma unroll 1
+    for (; i < i1; ++i, src += cols) {      // < kUnroll rows: the ring cannot overflow
+        visit(__ldcs(src));
+    }
+    drain(kChunk);
+    const uint32_t n_list = p4 >> 2;
+    drain(1u);                              // what is left (< kChunk keys) goes out as one more chunk
+    if (!live_col) return;
+
+#pragma unroll
+    for (int g = 0; g < M; ++g)
+        if (g < bp.n_groups && wd[g] != 0u && nlt[g]) atomicAdd(w.t_below + col * kMaxGroups + g, nlt[g]);
     w.s_cnt[(long long)blockIdx.y * cols + col] = min(n_list, cap);
     if (n_list > cap) atomicOr(w.t_ovf + col, 1u);
     named.flush(w, col);
@@ -785,14 +899,19 @@ template <int M, int NAMED>
 __global__ void __launch_bounds__(kBX)
 bracket_pass_kernel(const float* __restrict__ p, long long cols, long long rows,
                     long long rows_per_split, float eps, BracketPlan bp, Work w) {
-    __shared__ uint32_t stage[kBX * kStagePitch];
+    static_assert(kRing <= kStagePitch, "the staging area serves both bodies");
+    __shared__ __align__(128) uint32_t stage[kBX * kStagePitch];
     long long col = (long long)blockIdx.x * kBX + threadIdx.x;
     const bool live_col = col < cols;
     if (!live_col) col = cols - 1;          // keep the warp whole: it flushes rings cooperatively
     const long long i0 = (long long)blockIdx.y * rows_per_split;
     const long long i1 = min(rows, i0 + rows_per_split);
-    if (w.pending[8] == 0) bracket_pass_body<M, NAMED, true>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
-    else bracket_pass_body<M, NAMED, false>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
+    if (w.pending[8] == 0) {
+        if constexpr (M <= 4) bracket_pass_body_diff<M, NAMED>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
+        else bracket_pass_body<M, NAMED, true>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
+    } else {
+        bracket_pass_body<M, NAMED, false>(p, cols, col, live_col, i0, i1, eps, bp, w, stage);
+    }
 }
 
 template <int M>
@@ -1064,8 +1183,10 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
             }
             w.bk_lo[col * kMaxGroups + g] = lo;
             w.bk_hi[col * kMaxGroups + g] = hi;
-            // a bound that is a negative float (other than the open low end) rules out RAW mode
-            if (lo <= hi && ((lo != 0u && lo < 0x80000000u) || hi < 0x80000000u)) atomicOr(w.pending + 8, 1u);
+            // a bound that is a negative float (other than the open low end) rules out RAW mode, and so does a low
+            // bound of exactly +0 (key 0x80000000): RAW mode clamps negative values to +0, which must stay below
+            // every closed low bound
+            if (lo <= hi && ((lo != 0u && lo <= 0x80000000u) || hi < 0x80000000u)) atomicOr(w.pending + 8, 1u);
         }
     }
 }
@@ -1092,13 +1213,16 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     uint32_t* cnts = buf + M * kSelBuf;                // [splits]
     __shared__ uint32_t s_a[M], s_b[M], s_sh[M], s_below[M], s_first[M], s_nr[M], s_iv[M];
     __shared__ uint32_t s_bf[M], s_bl[M], s_cb[M], s_n[M], s_mode[M];
-    __shared__ int s_any;
+    // ranks of a bracket's region that lie beyond the bracket's keys move on to the gap after it
+    __shared__ uint32_t s_region[M], s_gap_hi[M], s_out_first[M], s_out_nr[M], s_out_below[M], s_out_cnt[M], s_keep[M];
+    __shared__ int s_any, s_rebuild;
 
     const long long col = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr int NW = kSelThreads / 32;
-    if (t < M) { s_mode[t] = SEL_IDLE; s_iv[t] = 0xFFFFFFFFu; s_n[t] = 0; s_a[t] = 0xFFFFFFFFu; s_b[t] = 0; s_sh[t] = 0; }
-    if (t == 0) s_any = 0;
+    if (t < M) { s_mode[t] = SEL_IDLE; s_iv[t] = 0xFFFFFFFFu; s_n[t] = 0; s_a[t] = 0xFFFFFFFFu; s_b[t] = 0; s_sh[t] = 0;
+                 s_out_nr[t] = 0; s_keep[t] = 1; }
+    if (t == 0) { s_any = 0; s_rebuild = 0; }
     __syncthreads();
     if (t == 0) {
         const uint32_t n_iv = w.n_iv[col];
@@ -1111,6 +1235,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
             s_a[g] = w.iv_klo[x]; s_b[g] = w.iv_khi[x];
             s_sh[g] = sel_shift(s_b[g] - s_a[g], kSelBins);
             s_below[g] = w.iv_below[x]; s_first[g] = w.iv_first[x]; s_nr[g] = w.iv_nr[x];
+            s_region[g] = w.t_cnt[col * kMaxGroups + g]; s_gap_hi[g] = w.t_gap_hi[col * kMaxGroups + g];
             s_mode[g] = SEL_HIST;
             s_any = 1;
         }
@@ -1189,10 +1314,31 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
             const uint32_t pre = inc - sum;
             const long long x = col * kMaxRanks + s_iv[g];
-            const uint32_t first = s_first[g], nr = s_nr[g], below = s_below[g], sh = s_sh[g];
+            const uint32_t first = s_first[g], below = s_below[g], sh = s_sh[g];
+            uint32_t nr = s_nr[g];
+            __syncwarp();
+            if (level == 0) {
+                // `total` is the number of keys inside the bracket: the ranks beyond them are in the gap that
+                // follows (the bracket missed them); they become a generic interval when the list is rebuilt
+                uint32_t nin = 0;
+                while (nin < nr && rp.rank[first + nin] - below < total) ++nin;
+                if (lane == 0) {
+                    w.iv_cnt[x] = total;
+                    if (nin < nr) {
+                        s_out_first[g] = first + nin; s_out_nr[g] = nr - nin;
+                        s_out_below[g] = below + total; s_out_cnt[g] = s_region[g] - total;
+                        s_nr[g] = nin; w.iv_nr[x] = nin;
+                        s_rebuild = 1;
+                        if (nin == 0) { s_keep[g] = 0; s_mode[g] = SEL_IDLE; }
+                    }
+                }
+                nr = nin;
+                __syncwarp();
+                if (nr == 0) continue;
+            }
             const uint32_t pos_f = rp.rank[first] - below;
             const uint32_t pos_l = rp.rank[first + nr - 1] - below;
-            const bool sane = pos_l < total && (level > 0 || total == w.iv_cnt[x]);
+            const bool sane = pos_l < total;
             if (sane && sh == 0) {
                 // bins are single keys: every rank reads its key off the histogram
                 for (uint32_t q = 0; q < nr; ++q) {
@@ -1268,7 +1414,31 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
         any_collect |= s_mode[g] == SEL_COLLECT;
         if (s_mode[g] == SEL_HIST && t == 0) atomicAdd(w.pending + 6, 1u);   // cannot happen (4 levels >= 32 bits)
     }
-    if (!any_collect) return;
+    // the interval list of the column with the gap intervals of missed ranks inserted in key order
+    auto rebuild = [&]() {
+        __syncthreads();
+        if (t != 0 || !s_rebuild) return;
+        IvList O, L;
+        iv_load(O, w, col);
+        L.n = 0;
+        for (uint32_t v = 0; v < O.n; ++v) {
+            int g = -1;
+            for (int q = 0; q < M; ++q) if (s_iv[q] == v) g = q;
+            if (g < 0 || s_keep[g]) {
+                const uint32_t i = L.n++;
+                L.klo[i] = O.klo[v]; L.khi[i] = O.khi[v]; L.shift[i] = O.shift[v]; L.below[i] = O.below[v];
+                L.status[i] = O.status[v]; L.first[i] = O.first[v]; L.nr[i] = O.nr[v]; L.cnt[i] = O.cnt[v];
+            }
+            if (g >= 0 && s_out_nr[g]) {
+                atomicAdd(w.pending + 2, s_out_nr[g]);
+                const unsigned long long glo = (unsigned long long)w.bk_hi[col * kMaxGroups + g] + 1ull;
+                iv_append(L, w, col, (uint32_t)glo, (unsigned long long)s_gap_hi[g] + 1ull - glo, s_out_below[g],
+                          s_out_cnt[g], s_out_first[g], s_out_nr[g], false, 0u);
+            }
+        }
+        iv_store(L, w, col);
+    };
+    if (!any_collect) { rebuild(); return; }
 
     // ---- second sweep: the keys of the target bins ----
     {   // key range of the target bins of every collecting bracket, in registers
@@ -1317,6 +1487,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
         }
         if (t == 0) w.iv_status[col * kMaxRanks + s_iv[g]] = IV_RESOLVED;
     }
+    rebuild();
 }
 
 // final rows: dB, numpy lerp, named statistics
