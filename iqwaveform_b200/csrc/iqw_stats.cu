@@ -795,10 +795,6 @@ __device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, l
 // INSIDE each bracket are not counted here: select_kernel counts them when it histograms the lists.
 constexpr int kRing = 32;                       // keys per thread: one chunk being filled, one being drained
 constexpr int kChunk = 16;                      // keys per drain
-#ifndef IQW_BP_PREFETCH
-#define IQW_BP_PREFETCH 48
-#endif
-constexpr int kPrefetchRows = IQW_BP_PREFETCH;  // L2 prefetch distance of the bracket pass, in rows (multiple of kUnroll; 0: off)
 
 template <int M, int NAMED>
 __device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__ p, long long cols, long long col,
@@ -827,7 +823,7 @@ __device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__
     Named<(NAMED & 1) != 0, (NAMED & 2) != 0, (NAMED & 4) != 0> named;
 
     auto drain = [&](uint32_t at_least) {
-        if ((p4 >> 2) - n_chunks * kChunk >= at_least) {
+        if (p4 - n_chunks * (4u * kChunk) >= 4u * at_least) {
             const uint4* q = reinterpret_cast<const uint4*>(my_stage + ((n_chunks & 1u) << 4));
             const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
             if ((n_chunks + 1u) * kChunk <= cap) {      // a full list keeps counting; the column is flagged below
@@ -853,28 +849,14 @@ __device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__
         for (int u = 0; u < kUnroll; ++u) visit(f[u]);
         drain(kChunk);          // at most kChunk - 1 + kUnroll < kRing keys are ever in the ring
     };
-    // One thread per CTA asks the L2 for the CTA's 512-byte row segments kPrefetchRows ahead (bulk prefetch, one
-    // instruction per row).
-    const bool pf_on = threadIdx.x == 0 && (cols & 3) == 0 && (long long)(blockIdx.x + 1) * kBX <= cols;
-    auto prefetch_block = [&](long long row) {     // rows row .. row + kUnroll - 1 of this CTA's column tile
-        if (kPrefetchRows > 0 && pf_on && row + kUnroll <= i1) {
-            const float* q = p + row * cols + (long long)blockIdx.x * kBX;
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u, q += cols)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(q), "r"((uint32_t)(kBX * sizeof(float))) : "memory");
-        }
-    };
-    for (int b = 2; b < kPrefetchRows / kUnroll; ++b) prefetch_block(i0 + (long long)b * kUnroll);
     if (i + kUnroll <= i1) load_block(fa);
 #pragma unroll 1
     while (i + kUnroll <= i1) {
         if (i + 2 * kUnroll <= i1) load_block(fb);
-        prefetch_block(i + kPrefetchRows);
         visit_block(fa);
         i += kUnroll;
         if (i + kUnroll > i1) break;
         if (i + 2 * kUnroll <= i1) load_block(fa);
-        prefetch_block(i + kPrefetchRows);
         visit_block(fb);
         i += kUnroll;
     }
@@ -895,6 +877,8 @@ __device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__
     named.flush(w, col);
 }
 
+// (no minimum-blocks bound: ptxas settles at 61 registers = 8 CTAs per SM by itself, and its schedule with an explicit
+// bound of 8 measured 1.92 instead of 1.74 ms)
 template <int M, int NAMED>
 __global__ void __launch_bounds__(kBX)
 bracket_pass_kernel(const float* __restrict__ p, long long cols, long long rows,
@@ -1216,6 +1200,11 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     // ranks of a bracket's region that lie beyond the bracket's keys move on to the gap after it
     __shared__ uint32_t s_region[M], s_gap_hi[M], s_out_first[M], s_out_nr[M], s_out_below[M], s_out_cnt[M], s_keep[M];
     __shared__ int s_any, s_rebuild;
+    // lookup of the sweeps: the live brackets in key order.  A key k can only belong to entry
+    // #{i >= 1 : k > s_thr[i]}, s_thr[i] = first key of entry i, minus one; unused thresholds are 0xFFFFFFFF
+    // (never exceeded), so that unused entries are never looked at.
+    __shared__ uint4 s_tbl[M + 1];          // x: first key, y: last key - first key, z: shift (sweep 1), w: offset / tag
+    __shared__ uint32_t s_thr[M + 1];
 
     const long long col = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -1269,31 +1258,34 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     for (int level = 0; level < 4; ++level) {
         // ---- histogram sweep over the brackets in SEL_HIST ----
         for (int i = t; i < M * kSelBins; i += kSelThreads) hist[i] = 0;
-        __syncthreads();
-        {   // bracket parameters in registers for the sweep (a bracket not in SEL_HIST gets an empty range)
-            // The brackets are disjoint, so a key feeds at most one histogram: the bin index is
-            // selected with predicated minima and ONE shared atomic follows (a branch and an atomic
-            // per bracket cost 57 instructions per key, this costs about half).  A bracket that is
-            // not being histogrammed gets the one-key range [0xFFFFFFFF, 0xFFFFFFFF] and an offset
-            // beyond the histograms, so that even that key cannot hide the match of a live bracket.
-            uint32_t ra[M], rw[M], rsh[M], goff[M];
-#pragma unroll
-            for (int g = 0; g < M; ++g) {
-                const bool on = s_mode[g] == SEL_HIST;
-                ra[g] = on ? s_a[g] : 0xFFFFFFFFu;
-                rw[g] = on ? s_b[g] - s_a[g] : 0u;          // k in [a, b]  <=>  k - a <= b - a (unsigned)
-                rsh[g] = on ? s_sh[g] : 0u;
-                goff[g] = on ? (uint32_t)(g * kSelBins) : 0x80000000u;
+        if (t == 0) {
+            int n = 0;
+            for (int g = 0; g < M; ++g) {       // brackets are in key order
+                if (s_mode[g] != SEL_HIST) continue;
+                s_tbl[n] = make_uint4(s_a[g], s_b[g] - s_a[g], s_sh[g], (uint32_t)(g * kSelBins));
+                s_thr[n] = s_a[g] - 1u;
+                ++n;
             }
-            sweep([&](uint32_t k) {
-                uint32_t idx = 0xFFFFFFFFu;
+            for (; n < M + 1; ++n) {
+                s_tbl[n] = make_uint4(0u, 0u, 0u, 0u);
+                s_thr[n] = 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();
+        {   // The brackets are disjoint, so a key feeds at most one histogram: three compares against the
+            // first keys of the live brackets pick the table entry, one 128-bit shared load fetches its
+            // parameters and ONE shared atomic follows (testing every bracket in turn cost 33 instructions
+            // per key, this costs about 15).
+            uint32_t thr[M];
 #pragma unroll
-                for (int g = 0; g < M; ++g) {
-                    const uint32_t d = k - ra[g];
-                    const uint32_t v = goff[g] + (d >> rsh[g]);
-                    if (d <= rw[g]) idx = min(idx, v);
-                }
-                if (idx < (uint32_t)(M * kSelBins)) atomicAdd(&hist[idx], 1u);
+            for (int i = 0; i < M; ++i) thr[i] = s_thr[i + 1];
+            sweep([&](uint32_t k) {
+                uint32_t j = 0;
+#pragma unroll
+                for (int i = 0; i + 1 < M; ++i) j += k > thr[i] ? 1u : 0u;
+                const uint4 e = s_tbl[j];
+                const uint32_t d = k - e.x;
+                if (d <= e.y) atomicAdd(&hist[e.w + (d >> e.z)], 1u);
             });
         }
         __syncthreads();
@@ -1441,27 +1433,37 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     if (!any_collect) { rebuild(); return; }
 
     // ---- second sweep: the keys of the target bins ----
-    {   // key range of the target bins of every collecting bracket, in registers
-        uint32_t ra[M], rw[M], tag[M];
-#pragma unroll
+    __syncthreads();
+    if (t == 0) {                          // the same lookup over the target bins of the collecting brackets
+        int n = 0;
         for (int g = 0; g < M; ++g) {
-            const bool on = s_mode[g] == SEL_COLLECT;
+            if (s_mode[g] != SEL_COLLECT) continue;
             const uint32_t sh = s_sh[g];
             const uint32_t lo = s_a[g] + (s_bf[g] << sh);
             unsigned long long hi = (unsigned long long)s_a[g] + (((unsigned long long)s_bl[g] + 1ull) << sh) - 1ull;
             if (hi > (unsigned long long)s_b[g]) hi = s_b[g];
-            ra[g] = on ? lo : 0xFFFFFFFFu;
-            rw[g] = on ? (uint32_t)hi - lo : 0u;
-            tag[g] = on ? (uint32_t)g : 0x80000000u;       // same scheme as the histogram sweep
+            s_tbl[n] = make_uint4(lo, (uint32_t)hi - lo, 0u, (uint32_t)g);
+            s_thr[n] = lo - 1u;
+            ++n;
         }
-        sweep([&](uint32_t k) {
-            uint32_t gm = 0xFFFFFFFFu;
+        for (; n < M + 1; ++n) {
+            s_tbl[n] = make_uint4(0u, 0u, 0u, 0u);
+            s_thr[n] = 0xFFFFFFFFu;
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t thr[M];
 #pragma unroll
-            for (int g = 0; g < M; ++g)
-                if (k - ra[g] <= rw[g]) gm = min(gm, tag[g]);
-            if (gm < (uint32_t)M) {
-                const uint32_t pos = atomicAdd(&s_n[gm], 1u);
-                if (pos < (uint32_t)kSelBuf) buf[gm * kSelBuf + pos] = k;
+        for (int i = 0; i < M; ++i) thr[i] = s_thr[i + 1];
+        sweep([&](uint32_t k) {
+            uint32_t j = 0;
+#pragma unroll
+            for (int i = 0; i + 1 < M; ++i) j += k > thr[i] ? 1u : 0u;
+            const uint4 e = s_tbl[j];
+            if (k - e.x <= e.y) {
+                const uint32_t pos = atomicAdd(&s_n[e.w], 1u);
+                if (pos < (uint32_t)kSelBuf) buf[e.w * kSelBuf + pos] = k;
             }
         });
     }
