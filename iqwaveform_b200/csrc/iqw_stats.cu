@@ -67,7 +67,10 @@ constexpr int kSubBins = 256;      // level-2 sub-bins of sample_brackets
 constexpr int kSelBuf = 2048;      // keys ranked in shared memory at the end of select
 constexpr int kSelThreads = 512;
 constexpr int kMaxSplits = 512;    // row splits of the bracket pass (select stages their counts)
-constexpr long long kBracketCtas = 148 * 64;   // CTAs the bracket pass aims at (a few waves)
+#ifndef IQW_BP_CTAS_PER_SM
+#define IQW_BP_CTAS_PER_SM 64
+#endif
+constexpr long long kBracketCtas = 148 * IQW_BP_CTAS_PER_SM;   // CTAs the bracket pass aims at (a few waves)
 constexpr long long kMinRowsPerSplit = 256;
 
 enum IvStatus : uint32_t { IV_REFINE = 0, IV_COLLECT = 1, IV_RESOLVED = 2, IV_SELECT = 3 };
@@ -1235,23 +1238,37 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
 
     const uint32_t cap_sum = bp.cap_sum;
     const bool raw = w.pending[8] == 0;     // lists hold raw float bits (bracket pass RAW mode)
-    auto sweep = [&](auto&& visit) {
-        const long long stride = cols * (long long)cap_sum;
-        const uint32_t* base = w.lists + (long long)col * cap_sum;
-        for (int sp = warp; sp < splits; sp += NW) {
+    // One warp per row split: rows of 32 keys.  Full rows go four at a time without predicates, the rest (up to
+    // three full rows and a partial one) under a bounds check.  `keep` = true leaves the lists in L2 for the
+    // second sweep (the lists of the CTAs in flight, ~110 MB, fit the 126 MB L2).
+    auto sweep = [&](bool keep, auto&& visit) {
+        const size_t stride = (size_t)cols * cap_sum;                       // keys between row splits
+        const uint32_t* src = w.lists + (size_t)col * cap_sum + (size_t)warp * stride + lane;
+        auto load = [&](const uint32_t* q) { return keep ? __ldcg(q) : __ldcs(q); };
+        auto key_of = [&](uint32_t v) { return raw ? float_to_key(__uint_as_float(v)) : v; };
+#pragma unroll 1
+        for (int sp = warp; sp < splits; sp += NW, src += stride * NW) {
             const uint32_t n = cnts[sp];
-            const uint32_t* src = base + (long long)sp * stride;
-            for (uint32_t i0 = 0; i0 < n; i0 += 256) {
-                uint32_t k[8];
+            const uint32_t full = n >> 5;
+            uint32_t r = 0;
+#pragma unroll 1
+            for (; r + 4 <= full; r += 4) {
+                uint32_t k[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t i = i0 + u * 32 + lane;
-                    k[u] = i < n ? __ldcs(src + i) : 0u;
-                }
+                for (int u = 0; u < 4; ++u) k[u] = load(src + (r + u) * 32u);
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (i0 + u * 32 + lane < n) visit(raw ? float_to_key(__uint_as_float(k[u])) : k[u]);
+                for (int u = 0; u < 4; ++u) visit(key_of(k[u]));
             }
+            uint32_t k[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                in[u] = (r + u) * 32u + lane < n;
+                k[u] = in[u] ? load(src + (r + u) * 32u) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (in[u]) visit(key_of(k[u]));
         }
     };
 
@@ -1279,7 +1296,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
             uint32_t thr[M];
 #pragma unroll
             for (int i = 0; i < M; ++i) thr[i] = s_thr[i + 1];
-            sweep([&](uint32_t k) {
+            sweep(true, [&](uint32_t k) {
                 uint32_t j = 0;
 #pragma unroll
                 for (int i = 0; i + 1 < M; ++i) j += k > thr[i] ? 1u : 0u;
@@ -1456,7 +1473,7 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
         uint32_t thr[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) thr[i] = s_thr[i + 1];
-        sweep([&](uint32_t k) {
+        sweep(false, [&](uint32_t k) {
             uint32_t j = 0;
 #pragma unroll
             for (int i = 0; i + 1 < M; ++i) j += k > thr[i] ? 1u : 0u;
