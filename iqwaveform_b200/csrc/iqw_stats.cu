@@ -60,7 +60,10 @@ constexpr int kBX = 128;           // columns (= threads) per CTA in the streami
 constexpr int kUnroll = 8;         // rows in flight per thread
 constexpr long long kSampleMinRows = 16384;   // below this the exact pipeline reads all rows
 constexpr int kSampleRows = 8192;  // rows of the sample staged in shared memory (per column)
-constexpr int kSampleCols = 2;     // columns per CTA of sample_brackets
+#ifndef IQW_SAMPLE_COLS
+#define IQW_SAMPLE_COLS 2
+#endif
+constexpr int kSampleCols = IQW_SAMPLE_COLS;     // columns per CTA of sample_brackets
 constexpr int kMaxGroups = 8;      // rank groups (brackets) per call on the sampled path
 constexpr int kSelBins = 2048;     // level-1 bins of sample_brackets and select
 constexpr int kSubBins = 256;      // level-2 sub-bins of sample_brackets
