@@ -336,6 +336,11 @@ static int launch2p(const StftArgs& a, int mode, cudaStream_t s) {
 // the logarithms of a mean of dB values run there, beside the FMA-bound transform of the producers.  stft_reduce_combine_kernel
 // (iqw_stft.cu) then combines the per-CTA rows.  Nothing is written per frame: 8 B/sample of HBM traffic.
 // ---------------------------------------------------------------------------------------------------
+static __device__ __noinline__ float power_to_dB_outlined(float p, float eps) { return power_to_dB(p, eps); }
+
+#ifndef IQW_RED_FLUSH
+#define IQW_RED_FLUSH 64
+#endif
 template <int LOG2N>
 struct P2RCfg {
     using B = P2Cfg<LOG2N, true>;
@@ -404,11 +409,22 @@ stft2p_reduce_kernel(const StftArgs a) {
             if (cnt[sl] < 0) cnt[sl] = 0;
             most = cnt[sl] > most ? cnt[sl] : most;
         }
+        // slots take consecutive frame ranges of (almost) equal length: slot sl has a frame in iteration `it` iff
+        // it < cnt[sl], and the counts do not increase with sl
+        long long cnt_min = cnt[PS - 1];
         int since = 0;
+        // |X|^2 >= 0, so |X|^2 + eps is a normal float whenever eps is one
+        const bool direct_lg2 = a.reduce_dB && a.eps >= 1.17549435e-38f;
+        const float sum_scale = direct_lg2 ? 3.01029995663981195f : 1.f;
         for (long long it = 0; it < most; ++it) {
+            int live = PS;          // slots with a frame in this iteration
+            if (it >= cnt_min) {
+                live = 0;
 #pragma unroll
-            for (int sl = 0; sl < PS; ++sl) {
-                if (it >= cnt[sl]) continue;
+                for (int sl = 0; sl < PS; ++sl) live += it < cnt[sl] ? 1 : 0;
+            }
+#pragma unroll 1
+            for (int sl = 0; sl < live; ++sl) {
                 mbar_wait(&full_bar[sl], (uint32_t)(it & 1));
                 const float* pt = ptiles + sl * N + ct;
                 // the tile is taken 16 values at a time (reading all 32 first and handing the tile back earlier was
@@ -426,26 +442,23 @@ stft2p_reduce_kernel(const StftArgs a) {
                         if (WMIN) mn[h + j] = fminf(mn[h + j], p[j]);
                     }
                     if (WSUM) {
-                        if (a.reduce_dB) {
-                            // branch-free lg2 of the quarter; zero / denormal / inf / nan arguments are rare and take
-                            // log10f behind one branch
-                            bool all_ok = true;
+                        if (a.reduce_dB && direct_lg2) {
+                            // p + eps is a normal float (or inf / nan, which lg2 passes on as numpy does): ONE lg2 per value,
+                            // summed in log2 units and scaled when the sum is flushed -- three instructions per value.  (The
+                            // split into exponent and mantissa that the spectrogram epilogue uses keeps every single value
+                            // within 5e-5 dB; a mean over frames does not need that, lg2.approx is within 2^-22 relative.)
 #pragma unroll
                             for (int j = 0; j < QB; ++j) {
-                                p[j] = fabsf(p[j]) + a.eps;
-                                all_ok &= dB_fast_ok(p[j]);
+                                float l;
+                                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(p[j] + a.eps));
+                                sm[h + j] += l;
                             }
-                            if (all_ok) {
+                        } else if (a.reduce_dB) {
+                            // eps is zero or denormal (not what the persistence spectrum passes): the checked logarithm,
+                            // out of line -- the consumers' loop must stay small, the instruction cache is shared with
+                            // the producers' transform
 #pragma unroll
-                                for (int j = 0; j < QB; ++j) { bool ok; sm[h + j] += power_to_dB_fast(p[j], ok); }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < QB; ++j) {
-                                    bool ok;
-                                    const float d = power_to_dB_fast(p[j], ok);
-                                    sm[h + j] += ok ? d : power_to_dB_slow(p[j]);
-                                }
-                            }
+                            for (int j = 0; j < QB; ++j) sm[h + j] += power_to_dB_outlined(p[j], a.eps);
                         } else {
 #pragma unroll
                             for (int j = 0; j < QB; ++j) sm[h + j] += p[j];
@@ -453,10 +466,10 @@ stft2p_reduce_kernel(const StftArgs a) {
                     }
                 }
                 if (WSUM) {
-                    if (++since == 64) {                                  // two-level summation
+                    if (++since == IQW_RED_FLUSH) {                       // two-level summation
                         since = 0;
 #pragma unroll
-                        for (int i = 0; i < BPT; ++i) { a.part_sum[part + ct + CT * i] += (double)sm[i]; sm[i] = 0.f; }
+                        for (int i = 0; i < BPT; ++i) { a.part_sum[part + ct + CT * i] += (double)(sm[i] * sum_scale); sm[i] = 0.f; }
                     }
                 }
             }
@@ -466,7 +479,7 @@ stft2p_reduce_kernel(const StftArgs a) {
             const long long k = part + ct + CT * i;
             a.part_max[k] = WMAX ? mx[i] : -INFINITY;
             a.part_min[k] = WMIN ? mn[i] : INFINITY;
-            if (WSUM) a.part_sum[k] += (double)sm[i];
+            if (WSUM) a.part_sum[k] += (double)(sm[i] * sum_scale);
             else a.part_sum[k] = 0.0;
         }
         return;

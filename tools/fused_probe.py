@@ -7,7 +7,7 @@ import bench
 dev = torch.device('cuda:0')
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000000
 x = bench.device_capture(torch, n, 1234, dev).view(1, n)
-for nfft in (4096, 2048, 1024):
+for nfft in [int(a) for a in sys.argv[2:]] or (4096, 2048, 1024):
     for stats, dB in ((['mean', 'max'], True), (['max'], True), (['mean', 'max', 'min'], True), (['mean', 'max'], False)):
         f = lambda: iqw.persistence_spectrum(x, fs=100e6, window='hann', resolution=100e6 / nfft, fractional_overlap=0.5,
                                              statistics=stats, dB=dB, axis=1)
