@@ -320,7 +320,8 @@ int iqw_debug_set_stft_scratch_cap(size_t bytes);
 
 /* Tuning aid: columns of at least this many rows take the sampled one-read path of iqw_time_stats_f32
  * (default 16384; 0 restores it); shorter ones the exact multi-pass pipeline.  Results are exact either way.
- * Set it before iqw_time_stats_workspace_bytes: the workspace layout depends on the path. */
+ * Set it before iqw_time_stats_workspace_bytes: the workspace layout depends on the path.
+ * A NEGATIVE value sets the sample size instead: rows / (-value) of a column, between 2048 and 8192 rows (default 8). */
 int iqw_debug_set_sample_min_rows(int64_t rows);
 
 /* Tuning aid: which kernel-1 geometry serves nfft 1024 / 2048 / 4096.  0 = automatic (the two-pass

@@ -1607,6 +1607,8 @@ static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPla
 static std::atomic<double> g_margin_sigmas{5.0};   // iqw_debug_set_sample_margin; 5 sigma: ~1 % of config-3 calls refine one column
 static std::atomic<int> g_margin_extra{2};
 static std::atomic<long long> g_sample_min_rows{kSampleMinRows};   // iqw_debug_set_sample_min_rows
+constexpr long long kSampleRowsMin = 2048;
+static std::atomic<long long> g_sample_share{8};                  // iqw_debug_set_sample_min_rows(-share)
 
 struct LongPlan {
     long long splits, rows_per_split;
@@ -1624,7 +1626,13 @@ static void plan_long_shape(int64_t rows, int64_t cols, LongPlan* lp) {
     // rps <= rows / 512 + 1 < 2^23 + 1 for rows < 2^32: the bracket pass counts rows in floats
     lp->rows_per_split = rps;
     lp->splits = (rows + rps - 1) / rps;
-    long long step = (rows + kSampleRows - 1) / kSampleRows;
+    // sample size: kSampleRows for long columns; shorter ones take rows / kSampleShare (at least kSampleRowsMin),
+    // because the sample pass costs as much per sampled row as the bracket pass per row and twice-wider brackets
+    // hardly matter when the whole matrix is small
+    long long want = rows / g_sample_share.load();
+    if (want < kSampleRowsMin) want = kSampleRowsMin;
+    if (want > kSampleRows) want = kSampleRows;
+    long long step = (rows + want - 1) / want;
     if (step < 2) step = 2;
     lp->sample = RowMap{rows / step, step, 0x9E3779B9u};
 }
@@ -1847,7 +1855,11 @@ extern "C" int iqw_debug_set_sample_margin(double sigmas, int extra) {
     return IQW_OK;
 }
 
+// rows > 0: columns of at least `rows` rows take the sampled path; rows < 0: the sample is rows / (-rows) of a
+// column (between kSampleRowsMin and kSampleRows rows); 0: both defaults
 extern "C" int iqw_debug_set_sample_min_rows(int64_t rows) {
+    if (rows < 0) { g_sample_share.store(-rows); return IQW_OK; }
+    if (rows == 0) g_sample_share.store(8);
     g_sample_min_rows.store(rows < 1 ? kSampleMinRows : rows);
     return IQW_OK;
 }

@@ -23,6 +23,15 @@ with_copy = bench._timed(torch, lambda: g(x), reps=10)
 print('graph replay %.4f ms (%.1f GS/s, %.3f of the measured HBM peak at 24 B/sample); with the input copy %.4f ms; identical: %s'
       % (graphed, n / graphed / 1e6, 24 * n / graphed / 1e6 / bench.measured_peak()[0], with_copy, bool(torch.equal(g(), ref))))
 
+# sample size: rows / share
+for share in (4, 8, 32):
+    _lib.lib.iqw_debug_set_sample_min_rows(-share)
+    pl = bench._timed(torch, lambda: iqw.persistence_spectrum(x, **kw), reps=10)
+    same = bool(torch.equal(iqw.persistence_spectrum(x, **kw), ref))
+    gs = iqw.GraphedCall(iqw.persistence_spectrum, x, **kw)
+    print('sample = rows / %d: plain %.4f ms, graph %.4f ms, identical %s' % (share, pl, bench._timed(torch, lambda: gs(), reps=10), same))
+_lib.lib.iqw_debug_set_sample_min_rows(0)
+
 # the exact multi-pass pipeline instead of the sampled one-read path (the 123 MB matrix fits the L2)
 _lib.lib.iqw_debug_set_sample_min_rows(1 << 30)
 ex = bench._timed(torch, lambda: iqw.persistence_spectrum(x, **kw), reps=10)
