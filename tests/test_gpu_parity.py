@@ -330,6 +330,39 @@ def test_sampled_path_is_exact_even_when_brackets_miss(cuda_device, sigmas, extr
     assert np.array_equal(got[:, 4], a.min(axis=1)) and np.array_equal(got[:, 5], a.max(axis=1))
 
 
+@pytest.mark.parametrize('sigmas,extra', [(0.0, 0), (0.5, 0), (5.0, 2)])
+def test_sampled_raw_mode_is_exact_when_brackets_miss(cuda_device, sigmas, extra):
+    """the same on data whose brackets are all non-negative: the bracket pass compares raw float bits (difference
+    form, negative values clamped), select counts the keys inside every bracket and moves ranks beyond them on to
+    the gap that follows.  A few negative values, signed zeros and +inf sit below / above every bracket."""
+    from iqwaveform_b200 import _lib
+    rng = np.random.default_rng(12)
+    T, nb = 120000, 136
+    a = np.abs(rng.standard_normal((1, T, nb))).astype(np.float32) + np.float32(0.01)
+    a[0, :, 0] = np.sort(a[0, :, 0])                       # trend: the row sample is biased
+    a[0, ::7919, 1] = -3.0                                 # 16 negative values: below every (positive) bracket
+    a[0, 5::9973, 1] = -0.0
+    a[0, :, 2] = np.round(a[0, :, 2] * 4) / 4 + 0.25       # few distinct values, heavy ties
+    a[0, :, 3] = 0.25                                      # constant
+    a[0, T // 2:, 4] += 50.0                               # level shift half way (bimodal)
+    a[0, :, 5] = np.exp(8 * a[0, :, 5])                    # 70 dB of dynamic range
+    a[0, 100, 6] = np.inf
+    qs = [0.01, 0.1, 0.5, 0.999]
+    cnt = []
+    try:
+        _lib.lib.iqw_debug_set_sample_margin(sigmas, extra)
+        got = iqw.time_statistics(dev_of(a, cuda_device), qs + ['min', 'max'], dB=False, counters=cnt).cpu().numpy()
+    finally:
+        _lib.lib.iqw_debug_set_sample_margin(5.0, 2)
+    want = np.quantile(a, np.array(qs, dtype=np.float32), axis=1)
+    for i in range(len(qs)):
+        assert np.array_equal(got[:, i], want[i]), (qs[i], np.argwhere(got[:, i] != want[i])[:5])
+    assert np.array_equal(got[:, 4], a.min(axis=1)) and np.array_equal(got[:, 5], a.max(axis=1))
+    assert cnt[0]['key_mode'] == 0 and cnt[0]['inconsistent'] == 0
+    if sigmas == 0.0:
+        assert cnt[0]['missed_ranks'] > nb // 4            # the fallback through the gap intervals really ran
+
+
 def test_long_path_with_many_brackets(cuda_device):
     """8 well separated single-rank statistics on a long matrix through the C-ABI: 8 brackets -> the
     M = 8 instantiations of the bracket pass (generic C++ body) and of select; negative data -> key
