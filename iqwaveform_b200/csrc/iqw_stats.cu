@@ -1241,37 +1241,39 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
 
     const uint32_t cap_sum = bp.cap_sum;
     const bool raw = w.pending[8] == 0;     // lists hold raw float bits (bracket pass RAW mode)
-    // One warp per row split: rows of 32 keys.  Full rows go four at a time without predicates, the rest (up to
-    // three full rows and a partial one) under a bounds check.  `keep` = true leaves the lists in L2 for the
-    // second sweep (the lists of the CTAs in flight, ~110 MB, fit the 126 MB L2).
+    // One warp per row split.  A lane reads FOUR consecutive keys with one 128-bit load (the lists are 128-byte
+    // aligned and a whole number of 16-key chunks long, so the load stays inside the list); two loads per lane
+    // are in flight, which covers the ~200 keys of a config-3 list in one round.  visit(key, live): keys past the
+    // end of the list are visited with live = false instead of branching around them.  `keep` = true leaves the
+    // lists in L2 for the second sweep (the lists of the CTAs in flight, ~110 MB, fit the 126 MB L2).
+    const uint32_t key_or = raw ? 0x80000000u : 0u, key_and = raw ? 0x7FFFFFFFu : 0u;
+    auto key_of = [&](uint32_t v) {        // raw float bits -> order-preserving key (identity in key mode)
+        return v ^ ((((uint32_t)((int32_t)v >> 31)) & key_and) | key_or);
+    };
     auto sweep = [&](bool keep, auto&& visit) {
         const size_t stride = (size_t)cols * cap_sum;                       // keys between row splits
-        const uint32_t* src = w.lists + (size_t)col * cap_sum + (size_t)warp * stride + lane;
-        auto load = [&](const uint32_t* q) { return keep ? __ldcg(q) : __ldcs(q); };
-        auto key_of = [&](uint32_t v) { return raw ? float_to_key(__uint_as_float(v)) : v; };
+        const uint32_t* src = w.lists + (size_t)col * cap_sum + (size_t)warp * stride + 4 * lane;
+        auto load = [&](const uint32_t* q) {
+            return keep ? __ldcg(reinterpret_cast<const uint4*>(q)) : __ldcs(reinterpret_cast<const uint4*>(q));
+        };
+        auto visit4 = [&](const uint4& q, uint32_t i, uint32_t n) {
+            visit(key_of(q.x), i < n);
+            visit(key_of(q.y), i + 1 < n);
+            visit(key_of(q.z), i + 2 < n);
+            visit(key_of(q.w), i + 3 < n);
+        };
 #pragma unroll 1
         for (int sp = warp; sp < splits; sp += NW, src += stride * NW) {
             const uint32_t n = cnts[sp];
-            const uint32_t full = n >> 5;
-            uint32_t r = 0;
 #pragma unroll 1
-            for (; r + 4 <= full; r += 4) {
-                uint32_t k[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) k[u] = load(src + (r + u) * 32u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) visit(key_of(k[u]));
+            for (uint32_t i0 = 4u * lane; i0 < n; i0 += 256u) {
+                const uint4 q0 = load(src + (i0 - 4u * lane));
+                const bool two = i0 + 128u < n;
+                uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
+                if (two) q1 = load(src + (i0 - 4u * lane) + 128u);
+                visit4(q0, i0, n);
+                if (two) visit4(q1, i0 + 128u, n);
             }
-            uint32_t k[4];
-            bool in[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                in[u] = (r + u) * 32u + lane < n;
-                k[u] = in[u] ? load(src + (r + u) * 32u) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (in[u]) visit(key_of(k[u]));
         }
     };
 
@@ -1299,13 +1301,13 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
             uint32_t thr[M];
 #pragma unroll
             for (int i = 0; i < M; ++i) thr[i] = s_thr[i + 1];
-            sweep(true, [&](uint32_t k) {
+            sweep(true, [&](uint32_t k, bool live) {
                 uint32_t j = 0;
 #pragma unroll
                 for (int i = 0; i + 1 < M; ++i) j += k > thr[i] ? 1u : 0u;
                 const uint4 e = s_tbl[j];
                 const uint32_t d = k - e.x;
-                if (d <= e.y) atomicAdd(&hist[e.w + (d >> e.z)], 1u);
+                if (live && d <= e.y) atomicAdd(&hist[e.w + (d >> e.z)], 1u);
             });
         }
         __syncthreads();
@@ -1476,12 +1478,12 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
         uint32_t thr[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) thr[i] = s_thr[i + 1];
-        sweep(false, [&](uint32_t k) {
+        sweep(false, [&](uint32_t k, bool live) {
             uint32_t j = 0;
 #pragma unroll
             for (int i = 0; i + 1 < M; ++i) j += k > thr[i] ? 1u : 0u;
             const uint4 e = s_tbl[j];
-            if (k - e.x <= e.y) {
+            if (live && k - e.x <= e.y) {
                 const uint32_t pos = atomicAdd(&s_n[e.w], 1u);
                 if (pos < (uint32_t)kSelBuf) buf[e.w * kSelBuf + pos] = k;
             }
