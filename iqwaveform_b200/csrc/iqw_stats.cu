@@ -1067,26 +1067,35 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
             if (c0 + c < cols) atomicAdd(&hist[c * kSelBins + ((keys[c * kSampleRows + i] - kmin[c]) >> sh1[c])], 1u);
     }
     __syncthreads();
-    {   // warp c scans column c: lane owns kSelBins/32 consecutive bins
-        const int c = t >> 5, lane = t & 31;
-        if (c < kSampleCols && c0 + c < cols) {
-            constexpr int PER = kSelBins / 32;
-            const uint32_t* h = hist + c * kSelBins + lane * PER;
-            uint32_t sum = 0;
+    {   // WPC warps scan a column (all sixteen warps work: two warps walking 64 bins per lane kept the other
+        // fourteen at the barrier for a fifth of the kernel's time); a lane owns PER consecutive bins
+        constexpr int WPC = kSampleThreads / 32 / kSampleCols;     // warps per column
+        constexpr int PER = kSelBins / (32 * WPC);
+        static_assert(kSelBins % (32 * WPC) == 0, "bins divide among the lanes of a column's warps");
+        __shared__ uint32_t s_wtot[kSampleCols][WPC];
+        const int c = (t >> 5) / WPC, wi = (t >> 5) % WPC, lane = t & 31;
+        const bool live = c0 + c < cols;
+        const uint32_t* h = hist + c * kSelBins + (wi * 32 + lane) * PER;
+        uint32_t sum = 0;
+        if (live)
             for (int b = 0; b < PER; ++b) sum += h[b];
-            uint32_t inc = sum;
+        uint32_t inc = sum;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += o;
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_wtot[c][wi] = inc;
+        __syncthreads();
+        if (live) {
             uint32_t cum = inc - sum;
+            for (int q = 0; q < wi; ++q) cum += s_wtot[c][q];
             int j = 0;
             while (j < nsr && bp.srank[j] < cum) ++j;
             for (int b = 0; b < PER && j < nsr; ++b) {
                 const uint32_t hb = h[b];
                 while (j < nsr && bp.srank[j] < cum + hb) {
-                    s_bin[c][j] = (uint32_t)(lane * PER + b);
+                    s_bin[c][j] = (uint32_t)((wi * 32 + lane) * PER + b);
                     s_below[c][j] = cum;
                     ++j;
                 }
