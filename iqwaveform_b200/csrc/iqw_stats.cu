@@ -1167,17 +1167,19 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
     if (t < kSampleCols && c0 + t < cols) {
         const long long col = c0 + t;
         int last = -1;
+        uint32_t last_hi = 0u;                                     // upper bound of slot `last` (kept in a register)
+        bool not_raw = false;
         for (int g = 0; g < kMaxGroups; ++g) {
             uint32_t lo = 0xFFFFFFFFu, hi = 0u;                    // empty slot
             if (g < bp.n_groups) {
                 lo = bp.s_lo[g] < 0 ? 0u : s_elo[t][bp.s_lo[g]];
                 hi = bp.s_hi[g] < 0 ? 0xFFFFFFFFu : s_ehi[t][bp.s_hi[g]];
                 if (hi < lo) hi = lo;
-                if (last >= 0 && lo <= w.bk_hi[col * kMaxGroups + last]) {
-                    if (hi > w.bk_hi[col * kMaxGroups + last]) w.bk_hi[col * kMaxGroups + last] = hi;
+                if (last >= 0 && lo <= last_hi) {
+                    if (hi > last_hi) { last_hi = hi; w.bk_hi[col * kMaxGroups + last] = hi; }
                     lo = 0xFFFFFFFFu; hi = 0u;
                 } else {
-                    last = g;
+                    last = g; last_hi = hi;
                 }
             }
             w.bk_lo[col * kMaxGroups + g] = lo;
@@ -1185,8 +1187,9 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
             // a bound that is a negative float (other than the open low end) rules out RAW mode, and so does a low
             // bound of exactly +0 (key 0x80000000): RAW mode clamps negative values to +0, which must stay below
             // every closed low bound
-            if (lo <= hi && ((lo != 0u && lo <= 0x80000000u) || hi < 0x80000000u)) atomicOr(w.pending + 8, 1u);
+            not_raw |= lo <= hi && ((lo != 0u && lo <= 0x80000000u) || hi < 0x80000000u);
         }
+        if (not_raw) atomicOr(w.pending + 8, 1u);
     }
 }
 
