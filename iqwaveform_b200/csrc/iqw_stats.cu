@@ -46,6 +46,7 @@
 // selection is exact for any input, ties and signed zeros included.  NaNs sort above +inf.
 #include <cmath>
 #include <atomic>
+#include <cooperative_groups.h>
 #include "iqw_common.cuh"
 
 namespace iqw {
@@ -463,9 +464,7 @@ __global__ void scan0_kernel(long long cols, RankPlan rp, Work w) {
     iv_store(L, w, col);
 }
 
-__global__ void scan_refine_kernel(long long cols, RankPlan rp, Work w) {
-    if (*w.pending == 0) return;
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ void scan_refine_body(long long col, long long cols, const RankPlan& rp, const Work& w) {
     if (col >= cols) return;
     IvList O, L;
     iv_load(O, w, col);
@@ -485,6 +484,11 @@ __global__ void scan_refine_kernel(long long cols, RankPlan rp, Work w) {
         split_by_subbuckets(L, O, v, w.hist1 + (col * kMaxRanks + v) * kNSub, rp, i, cum, w, col);
     }
     iv_store(L, w, col);
+}
+
+__global__ void scan_refine_kernel(long long cols, RankPlan rp, Work w) {
+    if (*w.pending == 0) return;
+    scan_refine_body((long long)blockIdx.x * blockDim.x + threadIdx.x, cols, rp, w);
 }
 
 // after the bracket pass (long-column path): the number of keys below every bracket is known, the number
@@ -591,20 +595,17 @@ struct IvRegs {
 
 // refine: 32 sub-buckets per pending interval, private counters [interval*32+sub][thread]
 template <int M>
-__global__ void __launch_bounds__(kBX)
-refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
-              Work w) {
-    if (*w.pending == 0) return;
-    extern __shared__ uint16_t hist[];   // [M*32][kBX]
+__device__ __forceinline__ void refine_body(unsigned bx, unsigned by, unsigned gdx, const float* __restrict__ p, long long cols,
+                                            RowMap rm, long long rows_per_split, const Work& w, uint16_t* hist /* [M*32][kBX] */) {
     const int t = threadIdx.x;
     const long long col_tiles = (cols + kBX - 1) / kBX;
-    const long long i0 = (long long)blockIdx.y * rows_per_split;
+    const long long i0 = (long long)by * rows_per_split;
     const long long i1 = min(rm.n, i0 + rows_per_split);
-    // a CTA owns the row range of blockIdx.y and walks column tiles blockIdx.x, + gridDim.x, ...;
+    // a CTA owns the row range of `by` and walks column tiles bx, + gdx, ...;
     // tiles without a pending interval cost one look at their interval lists.  (After the long
     // path only a few tiles are ever pending, so its launch uses few tile slots and many row
     // splits: the whole GPU then works on the one tile that needs it.)
-    for (long long tile = blockIdx.x; tile < col_tiles; tile += gridDim.x) {
+    for (long long tile = bx; tile < col_tiles; tile += gdx) {
         const long long col = tile * kBX + t;
         int active = 0;
         IvRegs<M> iv;
@@ -633,6 +634,16 @@ refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long 
         }
         __syncthreads();        // the private counters are zeroed again for the next tile
     }
+}
+
+// refine: 32 sub-buckets per pending interval, private counters [interval*32+sub][thread]
+template <int M>
+__global__ void __launch_bounds__(kBX)
+refine_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
+              Work w) {
+    if (*w.pending == 0) return;
+    extern __shared__ uint16_t hist[];   // [M*32][kBX]
+    refine_body<M>(blockIdx.x, blockIdx.y, gridDim.x, p, cols, rm, rows_per_split, w, hist);
 }
 
 // bracket pass (long-column path): the ONE read of all rows.  A thread owns a column; its M
@@ -905,14 +916,12 @@ bracket_pass_kernel(const float* __restrict__ p, long long cols, long long rows,
 }
 
 template <int M>
-__global__ void __launch_bounds__(kBX)
-collect_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
-               Work w) {
-    if (w.pending[1] == 0) return;
+__device__ __forceinline__ void collect_body(unsigned bx, unsigned by, unsigned gdx, const float* __restrict__ p,
+                                             long long cols, RowMap rm, long long rows_per_split, const Work& w) {
     const long long col_tiles = (cols + kBX - 1) / kBX;
-    const long long i0 = (long long)blockIdx.y * rows_per_split;
+    const long long i0 = (long long)by * rows_per_split;
     const long long i1 = min(rm.n, i0 + rows_per_split);
-    for (long long tile = blockIdx.x; tile < col_tiles; tile += gridDim.x) {     // see refine_kernel
+    for (long long tile = bx; tile < col_tiles; tile += gdx) {     // see refine_body
         const long long col = tile * kBX + threadIdx.x;
         int active = 0;
         IvRegs<M> iv;
@@ -933,17 +942,22 @@ collect_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long
     }
 }
 
+template <int M>
+__global__ void __launch_bounds__(kBX)
+collect_kernel(const float* __restrict__ p, long long cols, RowMap rm, long long rows_per_split,
+               Work w) {
+    if (w.pending[1] == 0) return;
+    collect_body<M>(blockIdx.x, blockIdx.y, gridDim.x, p, cols, rm, rows_per_split, w);
+}
+
 // ---------------------------------------------------------------------------------------------
 // resolve: one CTA per column; sort each COLLECT interval's candidates -> key of every rank
 // ---------------------------------------------------------------------------------------------
 constexpr int kResolveThreads = 256;
 
-__global__ void __launch_bounds__(kResolveThreads)
-resolve_kernel(long long cols, RankPlan rp, Work w) {
-    __shared__ uint32_t keys[kCap];
-    if (w.pending[1] == 0) return;
-    const long long col = blockIdx.x;
-    const int t = threadIdx.x;
+// (any block size: the tail kernel calls it with kBX threads)
+__device__ void resolve_body(long long col, const RankPlan& rp, const Work& w, uint32_t* keys /* [kCap] shared */) {
+    const int t = threadIdx.x, nt = blockDim.x;
     const uint32_t n_iv = w.n_iv[col];
     for (uint32_t v = 0; v < n_iv; ++v) {
         const long long x = col * kMaxRanks + v;
@@ -955,12 +969,12 @@ resolve_kernel(long long cols, RankPlan rp, Work w) {
         int m = 1;
         while (m < (int)n) m <<= 1;
         __syncthreads();
-        for (int i = t; i < m; i += kResolveThreads)
+        for (int i = t; i < m; i += nt)
             keys[i] = i < (int)n ? w.cand[x * kCap + i] : 0xFFFFFFFFu;
         __syncthreads();
         for (int k = 2; k <= m; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = t; i < m; i += kResolveThreads) {
+                for (int i = t; i < m; i += nt) {
                     const int ixj = i ^ j;
                     if (ixj > i) {
                         const uint32_t a = keys[i], b = keys[ixj];
@@ -976,6 +990,13 @@ resolve_kernel(long long cols, RankPlan rp, Work w) {
             w.r_key[col * kMaxRanks + first + t] = (sane && pos < n) ? keys[pos] : 0xFFFFFFFFu;
         }
     }
+}
+
+__global__ void __launch_bounds__(kResolveThreads)
+resolve_kernel(long long cols, RankPlan rp, Work w) {
+    __shared__ uint32_t keys[kCap];
+    if (w.pending[1] == 0) return;
+    resolve_body(blockIdx.x, rp, w, keys);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1527,9 +1548,8 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
 }
 
 // final rows: dB, numpy lerp, named statistics
-__global__ void finalize_kernel(long long rows, long long cols, StatPlan st, int to_dB, float eps,
-                                Work w, float* __restrict__ out /* [n_stats][cols] */) {
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void finalize_body(long long col, long long rows, long long cols, const StatPlan& st, int to_dB,
+                                              float eps, const Work& w, float* __restrict__ out /* [n_stats][cols] */) {
     if (col >= cols) return;
     auto xf = [&](uint32_t key) {
         const float v = key_to_float(key);
@@ -1566,6 +1586,72 @@ __global__ void finalize_kernel(long long rows, long long cols, StatPlan st, int
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+
+__global__ void finalize_kernel(long long rows, long long cols, StatPlan st, int to_dB, float eps,
+                                Work w, float* __restrict__ out /* [n_stats][cols] */) {
+    finalize_body((long long)blockIdx.x * blockDim.x + threadIdx.x, rows, cols, st, to_dB, eps, w, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// long-column path, everything after select in ONE cooperative launch: what select could not settle
+// from the candidate lists (missed brackets, overflowed lists, heavy ties; about one call in a hundred)
+// goes through the interval pipeline -- 7 x (refine, scan), collect, resolve -- with grid-wide barriers
+// between the steps, then the result rows are written.  When nothing is open the kernel goes straight to
+// the result rows: one launch where a train of 17 kernels used to exit one after the other (0.08 ms per
+// call, a seventh of the whole configs[0] call).  Every condition that guards a barrier is read from
+// memory while nobody writes it, so all CTAs take the same path.
+// ---------------------------------------------------------------------------------------------
+struct TailArgs {
+    const float* p;
+    long long rows, cols;
+    RowMap rm;
+    unsigned gx, gy;              // virtual grid of the refine / collect steps (tile slots x row splits)
+    long long rows_per_split;
+    RankPlan rp;
+    StatPlan st;
+    int to_dB;
+    float eps;
+    Work w;
+    float* out;
+};
+
+template <int M>
+__global__ void __launch_bounds__(kBX)
+tail_kernel(TailArgs a) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const Work& w = a.w;
+    const unsigned nvb = a.gx * a.gy;
+    const unsigned cblocks = (unsigned)((a.cols + kBX - 1) / kBX);
+    if ((w.pending[0] | w.pending[1]) != 0u) {          // select (the previous kernel) wrote them
+        for (int level = 0; level < kRefineLevels; ++level) {
+            const bool open = *w.pending != 0u;         // stable until the scan step below
+            // (virtual block vb = tile slot * row splits + row split: the row splits of a pending tile spread over ALL CTAs)
+            if (open)
+                for (unsigned vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+                    refine_body<M>(vb / a.gy, vb % a.gy, a.gx, a.p, a.cols, a.rm, a.rows_per_split, w,
+                                   reinterpret_cast<uint16_t*>(tail_smem));
+            grid.sync();
+            if (open)
+                for (unsigned vb = blockIdx.x; vb < cblocks; vb += gridDim.x)
+                    scan_refine_body((long long)vb * kBX + threadIdx.x, a.cols, a.rp, w);
+            grid.sync();
+        }
+        if (w.pending[1] != 0u) {                       // nobody writes it after the last scan step
+            for (unsigned vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+                collect_body<M>(vb / a.gy, vb % a.gy, a.gx, a.p, a.cols, a.rm, a.rows_per_split, w);
+            grid.sync();
+            for (long long col = blockIdx.x; col < a.cols; col += gridDim.x) {
+                resolve_body(col, a.rp, w, reinterpret_cast<uint32_t*>(tail_smem));
+                __syncthreads();
+            }
+        }
+        grid.sync();
+    }
+    for (unsigned vb = blockIdx.x; vb < cblocks; vb += gridDim.x)
+        finalize_body((long long)vb * kBX + threadIdx.x, a.rows, a.cols, a.st, a.to_dB, a.eps, w, a.out);
+}
+
 static int build_plans(const iqw_stat* stats, int n_stats, int64_t rows, RankPlan* rp, StatPlan* st,
                        bool* want_sum) {
     st->n_stats = n_stats;
@@ -1781,6 +1867,34 @@ static void launch_bracket_pass(cudaStream_t s, const float* p, long long cols, 
 #undef IQW_BP
 }
 
+// grid of the cooperative tail kernel: every CTA must be resident (a few per SM are plenty: its common case is
+// one pass over the result rows)
+template <int M>
+static int launch_tail(cudaStream_t s, const TailArgs& a, int sms) {
+    constexpr size_t smem_refine = sizeof(uint16_t) * M * kNSub * kBX, smem_keys = sizeof(uint32_t) * kCap;
+    constexpr size_t smem = smem_refine > smem_keys ? smem_refine : smem_keys;
+    static std::atomic<int> blocks_per_sm[64];          // per device; 0: not asked yet, -1: no cooperative launch
+    int dev = 0;
+    IQW_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return IQW_ERR_UNSUPPORTED;
+    int bps = blocks_per_sm[dev].load();
+    if (bps == 0) {
+        int coop = 0;
+        IQW_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        IQW_CUDA_OK(cudaFuncSetAttribute(tail_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IQW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, tail_kernel<M>, kBX, smem));
+        if (!coop || bps < 1) bps = -1;
+        else if (bps > 8) bps = 8;
+        blocks_per_sm[dev].store(bps);
+    }
+    if (bps < 0) return IQW_ERR_UNSUPPORTED;
+    TailArgs args = a;
+    void* params[] = {&args};
+    IQW_CUDA_OK(cudaLaunchCooperativeKernel((const void*)tail_kernel<M>, dim3((unsigned)(sms * bps)), dim3(kBX), params,
+                                            smem, s));
+    return IQW_OK;
+}
+
 template <int M>
 static int launch_select(cudaStream_t s, long long cols, const RankPlan& rp, const LongPlan& lp, const Work& w) {
     const size_t smem = sizeof(uint32_t) * ((size_t)M * (kSelBins + kSelBuf) + (size_t)lp.splits);
@@ -1969,15 +2083,24 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
                 g.grid = dim3((unsigned)slots, (unsigned)splits);
                 g.rows_per_split = rps;
             }
-            // the train that settles what select left open (it exits at once when nothing is):
-            // scan_brackets (above) + 7 x (refine, scan) + collect + resolve, then finalize
-            IQW_PROFILE_TRAIN("stats_tail", s, 1 + 2 * kRefineLevels + 3);
-            IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, n_cols, full, rp, w, cblocks, cthreads, "stats"));
-            IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, n_cols, full, w, "stats_collect"));
-            { IQW_PROFILE_FINE("stats_resolve", s);
-              resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_cols, rp, w); }
-            { IQW_PROFILE_FINE("stats_finalize", s);
-              finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, w, out); }
+            // what select left open (nothing, as a rule) and the result rows: one cooperative launch
+            TailArgs ta{p, n_rows, n_cols, full, g.grid.x, g.grid.y, g.rows_per_split, rp, st, to_dB, eps, w, out};
+            int rc_tail = IQW_OK;
+            { IQW_PROFILE("stats_tail", s);
+              IQW_DISPATCH_M(rp.n_ranks, rc_tail = launch_tail<M>(s, ta, sms)); }
+            if (rc_tail == IQW_ERR_UNSUPPORTED) {
+                // no cooperative launch on this device: the same steps as a train of kernels
+                // (7 x (refine, scan) + collect + resolve, then finalize; they exit at once when nothing is open)
+                IQW_PROFILE_TRAIN("stats_tail_train", s, 2 * kRefineLevels + 3);
+                IQW_DISPATCH_M(rp.n_ranks, launch_refine_levels<M>(g, s, p, n_cols, full, rp, w, cblocks, cthreads, "stats"));
+                IQW_DISPATCH_M(rp.n_ranks, launch_collect<M>(g, s, p, n_cols, full, w, "stats_collect"));
+                { IQW_PROFILE_FINE("stats_resolve", s);
+                  resolve_kernel<<<(unsigned)n_cols, kResolveThreads, 0, s>>>(n_cols, rp, w); }
+                { IQW_PROFILE_FINE("stats_finalize", s);
+                  finalize_kernel<<<cblocks, cthreads, 0, s>>>(n_rows, n_cols, st, to_dB, eps, w, out); }
+            } else if (rc_tail != IQW_OK) {
+                return rc_tail;
+            }
         }
         if (!sampled) {
             IQW_PROFILE("stats_finalize", s);
