@@ -75,7 +75,10 @@ constexpr int kMaxSplits = 512;    // row splits of the bracket pass (select sta
 #define IQW_BP_CTAS_PER_SM 64
 #endif
 constexpr long long kBracketCtas = 148 * IQW_BP_CTAS_PER_SM;   // CTAs the bracket pass aims at (a few waves)
-constexpr long long kMinRowsPerSplit = 256;
+#ifndef IQW_MIN_ROWS_PER_SPLIT
+#define IQW_MIN_ROWS_PER_SPLIT 512
+#endif
+constexpr long long kMinRowsPerSplit = IQW_MIN_ROWS_PER_SPLIT;
 
 enum IvStatus : uint32_t { IV_REFINE = 0, IV_COLLECT = 1, IV_RESOLVED = 2, IV_SELECT = 3 };
 
