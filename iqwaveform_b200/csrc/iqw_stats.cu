@@ -1255,25 +1255,25 @@ select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
                  s_out_nr[t] = 0; s_keep[t] = 1; }
     if (t == 0) { s_any = 0; s_rebuild = 0; }
     __syncthreads();
-    if (t == 0) {
-        const uint32_t n_iv = w.n_iv[col];
-        for (uint32_t v = 0; v < n_iv; ++v) {
-            const long long x = col * kMaxRanks + v;
-            if (w.iv_status[x] != IV_SELECT) continue;
-            const uint32_t g = w.iv_shift[x];
-            if (g >= (uint32_t)M) continue;
-            s_iv[g] = v;
-            s_a[g] = w.iv_klo[x]; s_b[g] = w.iv_khi[x];
-            s_sh[g] = sel_shift(s_b[g] - s_a[g], kSelBins);
-            s_below[g] = w.iv_below[x]; s_first[g] = w.iv_first[x]; s_nr[g] = w.iv_nr[x];
+    // one thread per interval of the column (their loads overlap; thread 0 alone walked several dependent load
+    // rounds per interval), the list lengths of the sweeps in the same round
+    if (t < kMaxRanks && (uint32_t)t < w.n_iv[col]) {
+        const long long x = col * kMaxRanks + t;
+        const uint32_t status = w.iv_status[x], g = w.iv_shift[x];
+        const uint32_t klo = w.iv_klo[x], khi = w.iv_khi[x], below = w.iv_below[x], first = w.iv_first[x], nr = w.iv_nr[x];
+        if (status == IV_SELECT && g < (uint32_t)M) {
+            s_iv[g] = (uint32_t)t;
+            s_a[g] = klo; s_b[g] = khi;
+            s_sh[g] = sel_shift(khi - klo, kSelBins);
+            s_below[g] = below; s_first[g] = first; s_nr[g] = nr;
             s_region[g] = w.t_cnt[col * kMaxGroups + g]; s_gap_hi[g] = w.t_gap_hi[col * kMaxGroups + g];
             s_mode[g] = SEL_HIST;
             s_any = 1;
         }
     }
+    for (int i = t; i < splits; i += kSelThreads) cnts[i] = w.s_cnt[(long long)i * cols + col];
     __syncthreads();
     if (!s_any) return;
-    for (int i = t; i < splits; i += kSelThreads) cnts[i] = w.s_cnt[(long long)i * cols + col];
 
     const uint32_t cap_sum = bp.cap_sum;
     const bool raw = w.pending[8] == 0;     // lists hold raw float bits (bracket pass RAW mode)
