@@ -58,7 +58,10 @@ constexpr int kNSub = 32;          // sub-buckets per interval and refinement le
 constexpr int kCap = 2048;         // candidates kept per (column, interval)
 constexpr int kRefineLevels = 7;   // 32 key bits / 5 bits per level
 constexpr int kBX = 128;           // columns (= threads) per CTA in the streaming passes
-constexpr int kUnroll = 8;         // rows in flight per thread
+#ifndef IQW_UNROLL
+#define IQW_UNROLL 8
+#endif
+constexpr int kUnroll = IQW_UNROLL;         // rows in flight per thread
 constexpr long long kSampleMinRows = 16384;   // below this the exact pipeline reads all rows
 constexpr int kSampleRows = 8192;  // rows of the sample staged in shared memory (per column)
 #ifndef IQW_SAMPLE_COLS
@@ -815,6 +818,12 @@ __device__ __forceinline__ void bracket_pass_body(const float* __restrict__ p, l
 // INSIDE each bracket are not counted here: select_kernel counts them when it histograms the lists.
 constexpr int kRing = 32;                       // keys per thread: one chunk being filled, one being drained
 constexpr int kChunk = 16;                      // keys per drain
+#ifndef IQW_BP_UNROLL
+#define IQW_BP_UNROLL 12
+#endif
+constexpr int kBpUnroll = IQW_BP_UNROLL;        // rows per block of the difference-form body (two blocks in flight):
+                                                // 8 / 12 / 16 rows measured 1.74 / 1.68 / 1.68 ms (61 / 72 / 87 registers)
+static_assert(kChunk - 1 + kBpUnroll < kRing, "the ring holds what a block can append before it is drained");
 
 template <int M, int NAMED>
 __device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__ p, long long cols, long long col,
@@ -859,29 +868,29 @@ __device__ __forceinline__ void bracket_pass_body_diff(const float* __restrict__
     };
     const float* src = p + i0 * cols + col;
     long long i = i0;
-    float fa[kUnroll], fb[kUnroll];
-    auto load_block = [&](float (&f)[kUnroll]) {
+    float fa[kBpUnroll], fb[kBpUnroll];
+    auto load_block = [&](float (&f)[kBpUnroll]) {
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u, src += cols) f[u] = __ldcs(src);
+        for (int u = 0; u < kBpUnroll; ++u, src += cols) f[u] = __ldcs(src);
     };
-    auto visit_block = [&](float (&f)[kUnroll]) {
+    auto visit_block = [&](float (&f)[kBpUnroll]) {
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) visit(f[u]);
-        drain(kChunk);          // at most kChunk - 1 + kUnroll < kRing keys are ever in the ring
+        for (int u = 0; u < kBpUnroll; ++u) visit(f[u]);
+        drain(kChunk);          // at most kChunk - 1 + kBpUnroll < kRing keys are ever in the ring
     };
-    if (i + kUnroll <= i1) load_block(fa);
+    if (i + kBpUnroll <= i1) load_block(fa);
 #pragma unroll 1
-    while (i + kUnroll <= i1) {
-        if (i + 2 * kUnroll <= i1) load_block(fb);
+    while (i + kBpUnroll <= i1) {
+        if (i + 2 * kBpUnroll <= i1) load_block(fb);
         visit_block(fa);
-        i += kUnroll;
-        if (i + kUnroll > i1) break;
-        if (i + 2 * kUnroll <= i1) load_block(fa);
+        i += kBpUnroll;
+        if (i + kBpUnroll > i1) break;
+        if (i + 2 * kBpUnroll <= i1) load_block(fa);
         visit_block(fb);
-        i += kUnroll;
+        i += kBpUnroll;
     }
 #pragma unroll 1
-    for (; i < i1; ++i, src += cols) {      // < kUnroll rows: the ring cannot overflow
+    for (; i < i1; ++i, src += cols) {      // < kBpUnroll rows: the ring cannot overflow
         visit(__ldcs(src));
     }
     drain(kChunk);
