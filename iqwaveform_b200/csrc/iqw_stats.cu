@@ -1053,7 +1053,10 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
     uint32_t mn[kSampleCols], mx[kSampleCols];
 #pragma unroll
     for (int c = 0; c < kSampleCols; ++c) { mn[c] = 0xFFFFFFFFu; mx[c] = 0u; }
-    constexpr int U = 8;                       // rows in flight per thread
+#ifndef IQW_SAMPLE_U
+#define IQW_SAMPLE_U 4
+#endif
+    constexpr int U = IQW_SAMPLE_U;            // rows in flight per thread
     for (int i0 = 0; i0 < S; i0 += kSampleThreads * U) {
         float v[U][kSampleCols];
 #pragma unroll
