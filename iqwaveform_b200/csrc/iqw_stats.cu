@@ -117,7 +117,8 @@ struct RowMap {
 __device__ __forceinline__ long long map_row(const RowMap& m, long long i) {
     uint32_t h = (uint32_t)i * 2654435761u + m.seed;
     h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-    return i * m.step + (long long)(h % (uint32_t)m.step);
+    // the jitter inside the stratum: high word of h * step (uniform in [0, step), one multiply instead of a division)
+    return i * m.step + (long long)__umulhi(h, (uint32_t)m.step);
 }
 
 // per-pipeline state, carved from the caller's workspace
@@ -1017,7 +1018,10 @@ resolve_kernel(long long cols, RankPlan rp, Work w) {
 // two-level histogram; the bracket bounds are bin edges (a little wider than the sample order
 // statistics, never narrower), which is all the bracket pass needs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSampleThreads = 512;
+#ifndef IQW_SAMPLE_THREADS
+#define IQW_SAMPLE_THREADS 512
+#endif
+constexpr int kSampleThreads = IQW_SAMPLE_THREADS;
 constexpr int kSR = 2 * kMaxGroups;   // sample ranks per column
 constexpr size_t kSampleSmem =
     sizeof(uint32_t) * ((size_t)kSampleCols * kSampleRows + (size_t)kSampleCols * kSR * kSubBins) +
