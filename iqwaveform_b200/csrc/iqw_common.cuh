@@ -91,36 +91,30 @@ __host__ __device__ __forceinline__ float key_to_float(uint32_t k) {
 }
 
 // 10*log10(|p| + eps) in float32 (power_analysis.py:199-204: abs, += eps, log10, *= 10).
-// log10 is evaluated as (e + log2(m)) * log10(2) with v = m * 2^e, m in [1, 2): MUFU.LG2 on the
-// mantissa alone has an absolute error of ~4e-7, i.e. ~1.2e-6 dB, far inside the 5e-5 dB parity
-// bound, at a third of the instructions of log10f.  Zero, denormal, infinite and NaN arguments take
-// log10f so that -inf / nan come out exactly as the reference's.
+// log10 is ONE `lg2.approx.ftz` times log10(2).  Measured over every exponent of the normal range
+// (tools/exp/lg2_accuracy.cu, 2^24 random arguments): the result is within one ulp of log2(v) -- 2.1e-7 for
+// |log2| < 1, 7.8e-6 at log2 = -111 -- i.e. at most 2.3e-5 dB at -334 dB and 1e-5 dB around +-100 dB, inside the
+// 5e-5 dB parity bound, at a fifth of the instructions of log10f.  (Rounds 1 and 2 split v = m * 2^e and took
+// lg2 of the mantissa alone: five more instructions per value for half an ulp.)  Zero, denormal, infinite and
+// NaN arguments take log10f so that -inf / nan come out exactly as the reference's.
 static __device__ __noinline__ float power_to_dB_slow(float v) { return 10.0f * log10f(v); }
 
 // the two halves of power_to_dB for kernels that convert many values per thread: a branch-free fast
 // path that is right whenever dB_fast_ok(v), so that the (rare) other arguments can be patched later
 __device__ __forceinline__ bool dB_fast_ok(float v) { return __float_as_uint(v) - 0x00800000u < 0x7F000000u; }
 __device__ __forceinline__ float power_to_dB_fast(float v /* = |p| + eps */, bool& ok) {
-    const uint32_t b = __float_as_uint(v);
-    ok = b - 0x00800000u < 0x7F000000u;
-    const float e = __uint_as_float(0x4B400000u | (b >> 23)) - 12583039.0f;
-    const float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    ok = dB_fast_ok(v);
     float l;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(m));
-    return (e + l) * 3.01029995663981195f;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+    return l * 3.01029995663981195f;
 }
 
 __device__ __forceinline__ float power_to_dB(float p, float eps) {
     const float v = fabsf(p) + eps;
-    const uint32_t b = __float_as_uint(v);
-    if (b - 0x00800000u < 0x7F000000u) {          // normal, finite, positive
-        // exponent as a float without I2F (which shares the quarter-rate XU pipe with MUFU):
-        // float(0x4B400000 | n) == 12582912 + n for n < 2^22
-        const float e = __uint_as_float(0x4B400000u | (b >> 23)) - 12583039.0f;
-        const float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (dB_fast_ok(v)) {                          // normal, finite, positive
         float l;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(m));     // m in [1, 2): never denormal
-        return (e + l) * 3.01029995663981195f;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+        return l * 3.01029995663981195f;
     }
     return power_to_dB_slow(v);                   // rare: out of line keeps the hot loops small
 }
