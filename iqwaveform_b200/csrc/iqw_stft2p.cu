@@ -207,19 +207,29 @@ stft2p_kernel(const StftArgs a) {
         if constexpr (MODE == IQW_STFT_DB) {
             // branch-free dB of all the thread's bins first (64 independent MUFU chains); the rare argument
             // that needs log10f (zero, denormal, inf, nan) is patched afterwards behind ONE branch per frame
-            bool all_ok = true;
+            // (|X|^2 + eps is a normal float, or inf / nan which lg2 passes on like log10f, whenever eps is a normal
+            // float: then nothing needs checking)
+            if (a.eps >= 1.17549435e-38f) {
 #pragma unroll
-            for (int i = 0; i < E; ++i) {
-                const float arg = fabsf(v[i].x * v[i].x + v[i].y * v[i].y) + a.eps;
-                bool ok;
-                const float d = power_to_dB_fast(arg, ok);
-                all_ok &= ok;
-                v[i] = make_float2(d, arg);
-            }
-            if (!all_ok) {
+                for (int i = 0; i < E; ++i) {
+                    bool ok;
+                    v[i].x = power_to_dB_fast(v[i].x * v[i].x + v[i].y * v[i].y + a.eps, ok);
+                }
+            } else {
+                bool all_ok = true;
 #pragma unroll
-                for (int i = 0; i < E; ++i)
-                    if (!dB_fast_ok(v[i].y)) v[i].x = power_to_dB_slow(v[i].y);
+                for (int i = 0; i < E; ++i) {
+                    const float arg = fabsf(v[i].x * v[i].x + v[i].y * v[i].y) + a.eps;
+                    bool ok;
+                    const float d = power_to_dB_fast(arg, ok);
+                    all_ok &= ok;
+                    v[i] = make_float2(d, arg);
+                }
+                if (!all_ok) {
+#pragma unroll
+                    for (int i = 0; i < E; ++i)
+                        if (!dB_fast_ok(v[i].y)) v[i].x = power_to_dB_slow(v[i].y);
+                }
             }
         }
 #pragma unroll
