@@ -2084,7 +2084,7 @@ extern "C" int iqw_time_stats_f32(const float* d_p, int64_t n_channels, int64_t 
               sample_brackets_kernel<<<(unsigned)((n_cols + kSampleCols - 1) / kSampleCols), kSampleThreads,
                                        kSampleSmem, s>>>(p, n_cols, lp.sample, lp.bp, w); }
             IQW_DISPATCH_G(lp.bp.n_groups, launch_bracket_pass<M>(s, p, n_cols, n_rows, lp, want_minmax, want_sum, to_dB != 0, eps, w));
-            { IQW_PROFILE_FINE("stats_scan", s);
+            { IQW_PROFILE("stats_scan", s);
               scan_brackets_kernel<<<cblocks, cthreads, 0, s>>>(n_cols, n_rows, rp, lp.bp.n_groups, w); }
             IQW_DISPATCH_G(lp.bp.n_groups, if (int rc = launch_select<M>(s, n_cols, rp, lp, w)) return rc);
             // whatever select could not settle from the lists (missed brackets, overflowed lists,
