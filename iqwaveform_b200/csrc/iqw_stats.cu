@@ -1909,8 +1909,11 @@ static int launch_tail(cudaStream_t s, const TailArgs& a, int sms) {
     if (bps < 0) return IQW_ERR_UNSUPPORTED;
     TailArgs args = a;
     void* params[] = {&args};
-    IQW_CUDA_OK(cudaLaunchCooperativeKernel((const void*)tail_kernel<M>, dim3((unsigned)(sms * bps)), dim3(kBX), params,
-                                            smem, s));
+    if (cudaLaunchCooperativeKernel((const void*)tail_kernel<M>, dim3((unsigned)(sms * bps)), dim3(kBX), params, smem, s) !=
+        cudaSuccess) {
+        (void)cudaGetLastError();           // e.g. the grid cannot be co-resident right now: the caller runs the train
+        return IQW_ERR_UNSUPPORTED;
+    }
     return IQW_OK;
 }
 
