@@ -71,8 +71,17 @@ constexpr int kSampleCols = IQW_SAMPLE_COLS;     // columns per CTA of sample_br
 constexpr int kMaxGroups = 8;      // rank groups (brackets) per call on the sampled path
 constexpr int kSelBins = 2048;     // level-1 bins of sample_brackets and select
 constexpr int kSubBins = 256;      // level-2 sub-bins of sample_brackets
-constexpr int kSelBuf = 2048;      // keys ranked in shared memory at the end of select
-constexpr int kSelThreads = 512;
+#ifndef IQW_SEL_BUF
+#define IQW_SEL_BUF 2048
+#endif
+#ifndef IQW_SEL_THREADS
+#define IQW_SEL_THREADS 512
+#endif
+#ifndef IQW_SEL_MINBLOCKS
+#define IQW_SEL_MINBLOCKS 3
+#endif
+constexpr int kSelBuf = IQW_SEL_BUF;      // keys ranked in shared memory at the end of select
+constexpr int kSelThreads = IQW_SEL_THREADS;
 constexpr int kMaxSplits = 512;    // row splits of the bracket pass (select stages their counts)
 #ifndef IQW_BP_CTAS_PER_SM
 #define IQW_BP_CTAS_PER_SM 64
@@ -1247,7 +1256,7 @@ sample_brackets_kernel(const float* __restrict__ p, long long cols, RowMap rm, B
 enum SelMode : uint32_t { SEL_IDLE = 0, SEL_HIST = 1, SEL_COLLECT = 2 };
 
 template <int M>
-__global__ void __launch_bounds__(kSelThreads, 3)
+__global__ void __launch_bounds__(kSelThreads, IQW_SEL_MINBLOCKS)
 select_kernel(long long cols, int splits, RankPlan rp, BracketPlan bp, Work w) {
     extern __shared__ uint32_t smem_u32[];
     uint32_t* hist = smem_u32;                         // [M][kSelBins]
